@@ -1,0 +1,173 @@
+/*
+ * opv.h -- C ABI of libopv_sm100.so, the B200 (sm_100a) engine for the OpenProvence
+ * scoring-and-pruning hot path.
+ *
+ * The library replaces, for that path only, what the reference reaches through
+ *   OpenProvenceModel.forward            open_provence/modeling_open_provence_standalone.py:1666-1739
+ *   OpenProvenceEncoder.forward          open_provence/encoder.py:174-245
+ *   the HF ModernBERT layer stack        transformers/models/modernbert/modeling_modernbert.py:52-634
+ *   score conversion + sentence prune    open_provence/modeling_open_provence_standalone.py:2893-2924,3065-3136
+ *
+ * Conventions
+ *   - plain C types only; every pointer named d_* is a DEVICE pointer, h_* a HOST pointer
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream
+ *     and never synchronises; the caller owns all buffers (weights, workspace, outputs)
+ *   - every function returns 0 on success and a negative opv_status on failure;
+ *     opv_last_error() returns a thread-local, human readable description
+ *   - sequences are packed without padding: token t of sequence s lives at row
+ *     cu_seqlens[s] + t of every [T, ...] buffer (the reference pads to the longest row of the
+ *     batch instead, standalone:2832-2880; values at padded positions are never read there)
+ *
+ * Reference-side binding: see INTEGRATION.md (ctypes stub that swaps OpenProvenceModel.forward).
+ */
+#ifndef OPV_H_
+#define OPV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPV_ABI_VERSION 1
+#define OPV_MAX_LAYERS 64
+
+typedef enum opv_status {
+  OPV_OK = 0,
+  OPV_ERR_INVALID_ARGUMENT = -1, /* ValueError on the Python side */
+  OPV_ERR_UNSUPPORTED = -2,      /* architecture / shape outside what the kernels implement */
+  OPV_ERR_CUDA = -3,             /* a CUDA runtime / driver call failed */
+  OPV_ERR_WORKSPACE = -4         /* workspace too small for this call */
+} opv_status;
+
+/* Arithmetic mode of the GEMM / attention operands (accumulation, residual stream, LayerNorm,
+ * softmax and GELU are always fp32). */
+typedef enum opv_dtype {
+  OPV_DTYPE_BF16 = 0, /* tcgen05 kind::f16 tensor-core path (the product path) */
+  OPV_DTYPE_F32 = 1   /* FFMA parity mode (1e-5 against the fp32 reference forward) */
+} opv_dtype;
+
+/* What HF's ModernBertConfig carries for the backbone (configuration_modernbert.py:77-167) plus
+ * the OpenProvence head sizes (standalone:1246-1302). */
+typedef struct opv_config {
+  int32_t abi_version;          /* must be OPV_ABI_VERSION */
+  int32_t hidden_size;          /* H; multiple of 128 */
+  int32_t num_layers;           /* L <= OPV_MAX_LAYERS */
+  int32_t num_heads;            /* H / 64 (head_dim must be 64) */
+  int32_t intermediate_size;    /* I; multiple of 128 */
+  int32_t vocab_size;           /* V */
+  int32_t num_labels;           /* ranking labels (1 for the published checkpoints) */
+  int32_t local_window;         /* config.local_attention (128): keys with |i-j| <= local_window/2 */
+  int32_t max_positions;        /* rows of the RoPE tables */
+  float norm_eps;               /* 1e-5 */
+  int32_t dtype;                /* opv_dtype */
+  int32_t fuse_epilogues;       /* bf16 only: 1 = RoPE/GeGLU/residual fused into the GEMM epilogues */
+  uint8_t layer_is_global[OPV_MAX_LAYERS]; /* 1 = full attention, 0 = sliding window */
+} opv_config;
+
+/* Device pointers of one encoder layer (HF:313-342). Matrices are nn.Linear weights, [out, in]
+ * row-major, in the operand dtype (bf16 or f32). */
+typedef struct opv_layer_weights {
+  const float* d_attn_norm; /* [H] or NULL for layer 0 (HF:318-319) */
+  const void* d_wqkv;       /* [3H, H]  rows = [q heads | k heads | v heads] (HF:280-282) */
+  const void* d_wo;         /* [H, H] */
+  const float* d_mlp_norm;  /* [H] */
+  const void* d_wi;         /* [2I, H]; when fuse_epilogues: rows interleaved in blocks of 128,
+                               [in 0:128 | gate 0:128 | in 128:256 | gate 128:256 | ...] */
+  const void* d_wo2;        /* [H, I] */
+} opv_layer_weights;
+
+typedef struct opv_weights {
+  const void* d_tok_embeddings;  /* [V, H] operand dtype */
+  const float* d_emb_norm;       /* [H] */
+  const float* d_final_norm;     /* [H] */
+  const float* d_head_dense;     /* [H, H] fp32 (HF:496) */
+  const float* d_head_norm;      /* [H] */
+  const float* d_cls_weight;     /* [num_labels, H] fp32 (HF:608) */
+  const float* d_cls_bias;       /* [num_labels] */
+  const float* d_prune_weight;   /* [2, H] fp32 (standalone:420) */
+  const float* d_prune_bias;     /* [2] */
+  const float* d_rope_cos_global; /* [max_positions, 32] fp32, built exactly as HF:139-172 */
+  const float* d_rope_sin_global;
+  const float* d_rope_cos_local;
+  const float* d_rope_sin_local;
+  const opv_layer_weights* h_layers; /* HOST array of num_layers entries (copied by opv_create) */
+} opv_weights;
+
+typedef struct opv_engine* opv_handle;
+
+const char* opv_last_error(void);
+int opv_abi_version(void);
+
+/* Create an engine bound to CUDA device `device`.  Weight pointers are borrowed: the caller keeps
+ * the tensors alive until opv_destroy. */
+int opv_create(const opv_config* cfg, const opv_weights* w, int device, opv_handle* out);
+int opv_destroy(opv_handle h);
+
+/* Bytes of scratch the forward needs for up to max_tokens packed tokens / max_seqs sequences. */
+size_t opv_workspace_bytes(opv_handle h, int64_t max_tokens, int32_t max_seqs);
+
+/* The forward (replaces standalone:1666-1739 on packed input).
+ *   d_ids        int32 [T]        token ids
+ *   d_cu_seqlens int32 [n+1]      prefix sums of sequence lengths, cu[0]=0, cu[n]=T
+ *   d_prune_logits fp32 [T, 2]    == pruning_logits on valid tokens
+ *   d_rank_logits  fp32 [n, num_labels] == ranking_logits
+ */
+int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_seqlens, int32_t n_seqs,
+                       int64_t n_tokens, int32_t max_seqlen, float* d_prune_logits, float* d_rank_logits,
+                       void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Score conversion + per-fragment mean (standalone:2913-2920, 3075-3082).
+ *   keep-prob p[t] = softmax(prune_logits[t])[1]; frag_mean[f] = mean(p[start_f:end_f]) or 1.0 when the
+ *   range is empty; rank_score[s] = sigmoid(rank_logits[s, 0]).
+ *   d_frag_ranges int32 [F, 2]  packed-token [start, end) per fragment
+ */
+int opv_fragment_means(const float* d_prune_logits, int64_t n_tokens, const int32_t* d_frag_ranges,
+                       int32_t n_frags, float* d_frag_mean, const float* d_rank_logits, int32_t n_seqs,
+                       int32_t num_labels, float* d_rank_score, void* stream);
+
+/* Per-sentence prune (standalone:3094-3134 without the string work).
+ *   sentence s owns fragment means d_frag_mean[d_sent_frag_index[k]] for k in
+ *   [d_sent_offsets[s], d_sent_offsets[s+1]); prob = mean (fp64) clamped to [0,1], 0.0 when it has none;
+ *   keep = prob > threshold.  d_near flags |prob - threshold| <= guard so the host can re-evaluate those
+ *   few sentences with the reference's exact numpy procedure.
+ */
+int opv_sentence_prune(const float* d_frag_mean, const int32_t* d_sent_offsets, const int32_t* d_sent_frag_index,
+                       int32_t n_sents, double threshold, double guard, double* d_sent_prob, uint8_t* d_keep,
+                       uint8_t* d_near, void* stream);
+
+/* ---- single-op entry points (unit tests, profiling) ------------------------------------------- */
+
+typedef enum opv_epilogue {
+  OPV_EPI_STORE = 0,    /* C = A.W^T                                (C operand dtype)            */
+  OPV_EPI_ROPE = 1,     /* C = rope(A.W^T) on the q,k thirds         (needs d_pos, cos/sin)       */
+  OPV_EPI_RESIDUAL = 2, /* R += A.W^T                                (R fp32 [M, N])              */
+  OPV_EPI_GEGLU = 3     /* C[:, j] = gelu(u[:, in_j]) * u[:, gate_j] (W rows interleaved, C [M, N/2]) */
+} opv_epilogue;
+
+/* C = epilogue(A[M,K] . W[N,K]^T). dtype selects the tcgen05 (bf16) or FFMA (f32) kernel. */
+int opv_op_gemm(int32_t dtype, int32_t epilogue, const void* d_a, const void* d_w, void* d_c, int64_t m, int32_t n,
+                int32_t k, const int32_t* d_pos, const float* d_cos, const float* d_sin, int32_t hidden_size,
+                void* stream);
+/* x = LN(h) * w ; out operand dtype. h fp32 [M, H]. */
+int opv_op_layernorm(int32_t dtype, const float* d_h, const float* d_w, void* d_out, int64_t m, int32_t hidden,
+                     float eps, void* stream);
+/* h = LN(E[ids]) * w (fp32) and x = cast(h). */
+int opv_op_embed_ln(int32_t dtype, const int32_t* d_ids, const void* d_emb, const float* d_w, float* d_h,
+                    void* d_x, int64_t m, int32_t hidden, int32_t vocab, float eps, void* stream);
+/* Varlen attention over packed qkv [T, 3H] (RoPE already applied) -> out [T, H]. window < 0 = global. */
+int opv_op_attention(int32_t dtype, const void* d_qkv, void* d_out, const int32_t* d_cu_seqlens, int32_t n_seqs,
+                     int32_t max_seqlen, int32_t num_heads, int32_t half_window, void* stream);
+/* In-place RoPE on the q,k thirds of qkv [T, 3H] (unfused path). */
+int opv_op_rope(int32_t dtype, void* d_qkv, const int32_t* d_pos, const float* d_cos, const float* d_sin,
+                int64_t m, int32_t hidden, void* stream);
+/* act[:, j] = gelu(u[:, j]) * u[:, I + j]; u [M, 2I] in HF order (unfused path). */
+int opv_op_geglu(int32_t dtype, const void* d_u, void* d_act, int64_t m, int32_t intermediate, void* stream);
+/* pos[t] = t - cu_seqlens[seq(t)] */
+int opv_op_positions(const int32_t* d_cu_seqlens, int32_t n_seqs, int32_t* d_pos, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPV_H_ */

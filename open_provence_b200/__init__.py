@@ -1,0 +1,12 @@
+"""open_provence_b200 -- B200 (sm_100a) engine for OpenProvence's scoring-and-pruning hot path.
+
+Only what the hot path needs lives here:
+  csrc/        hand-written CUDA for sm_100a + the C ABI (include/opv.h)
+  _native.py   ctypes binding of libopv_sm100.so (no fallback)
+  engine.py    weight packing + launches
+  modeling.py  drop-in ``OpenProvenceModel`` (from_pretrained / forward / process)
+"""
+
+__version__ = "0.1.0"
+
+__all__ = ["__version__"]

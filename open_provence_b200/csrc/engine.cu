@@ -1,0 +1,599 @@
+// libopv_sm100.so -- C ABI (include/opv.h) and host-side launch sequence of the ModernBERT forward.
+//
+// One engine per (process, device).  Everything is enqueued on the caller's stream; nothing here
+// synchronises or allocates device memory (weights, workspace and outputs belong to the caller).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/opv.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tcgen05.cuh"
+#include "pointwise.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define OPV_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t err__ = (expr);                                                                     \
+    if (err__ != cudaSuccess)                                                                       \
+      return fail(OPV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, \
+                  __LINE__);                                                                        \
+  } while (0)
+
+#define OPV_LAUNCH_CHECK(name)                                                                     \
+  do {                                                                                             \
+    cudaError_t err__ = cudaGetLastError();                                                        \
+    if (err__ != cudaSuccess)                                                                      \
+      return fail(OPV_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(err__));       \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors: cuTensorMapEncodeTiled is fetched through the runtime so the library does not
+// link libcuda (the build box has no driver).
+// ------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    OPV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr)
+      return fail(OPV_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cached = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  *out = cached;
+  return OPV_OK;
+}
+
+// 2D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols] with 128 B swizzle.
+int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn encode;
+  if (int rc = get_encode_fn(&encode)) return rc;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(OPV_ERR_INVALID_ARGUMENT, "TMA base not 16 B aligned");
+  if (cols % 8 != 0) return fail(OPV_ERR_INVALID_ARGUMENT, "TMA row pitch must be a multiple of 16 B");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(opv::kGemmBlockK), box_rows};
+  cuuint32_t elem[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, elem,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OPV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return OPV_OK;
+}
+
+int g_num_sms = 0;
+bool g_attrs_set = false;
+
+template <int BLOCK_N, int EPI>
+int set_gemm_attr() {
+  OPV_CUDA(cudaFuncSetAttribute(opv::gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, opv::GemmSmemLayout<BLOCK_N>::kTotal));
+  return OPV_OK;
+}
+
+int ensure_device_setup() {
+  if (g_attrs_set) return OPV_OK;
+  int dev = 0;
+  OPV_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  OPV_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(OPV_ERR_UNSUPPORTED, "libopv_sm100 needs an sm_100 (B200) device, found sm_%d%d", prop.major,
+                prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+  if (int rc = set_gemm_attr<256, opv::kEpiStore>()) return rc;
+  if (int rc = set_gemm_attr<256, opv::kEpiRope>()) return rc;
+  if (int rc = set_gemm_attr<256, opv::kEpiResidual>()) return rc;
+  if (int rc = set_gemm_attr<256, opv::kEpiGeglu>()) return rc;
+  if (int rc = set_gemm_attr<128, opv::kEpiStore>()) return rc;
+  if (int rc = set_gemm_attr<128, opv::kEpiRope>()) return rc;
+  if (int rc = set_gemm_attr<128, opv::kEpiResidual>()) return rc;
+  g_attrs_set = true;
+  return OPV_OK;
+}
+
+template <int BLOCK_N, int EPI>
+int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const opv::GemmEpilogueArgs& ep, int64_t M,
+                   int N, int K, cudaStream_t stream) {
+  const int64_t tiles = ((M + opv::kGemmBlockM - 1) / opv::kGemmBlockM) * (N / BLOCK_N);
+  const int grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+  opv::gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>
+      <<<grid, opv::kGemmThreads, opv::GemmSmemLayout<BLOCK_N>::kTotal, stream>>>(tm_a, tm_b, ep, (int)M, N, K);
+  OPV_LAUNCH_CHECK("gemm_bf16_tcgen05_kernel");
+  return OPV_OK;
+}
+
+int gemm_block_n(int N, int epi) {
+  if (epi == opv::kEpiGeglu) return (N % 256 == 0) ? 256 : 0;
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  return 0;
+}
+
+// A: [M, K] bf16 activations, W: [N, K] bf16 weight (tensor map with box rows = BLOCK_N)
+int gemm_bf16(int epi, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const opv::GemmEpilogueArgs& ep, int64_t M,
+              int N, int K, cudaStream_t stream) {
+  if (M <= 0) return OPV_OK;
+  if (M > 0x7fffff00LL) return fail(OPV_ERR_UNSUPPORTED, "M = %lld rows exceeds the int32 tile range", (long long)M);
+  if (K % opv::kGemmBlockK != 0) return fail(OPV_ERR_UNSUPPORTED, "K = %d must be a multiple of 64", K);
+  const int bn = gemm_block_n(N, epi);
+  if (bn == 0) return fail(OPV_ERR_UNSUPPORTED, "N = %d must be a multiple of 128 (256 for GeGLU)", N);
+  if (bn == 256) {
+    switch (epi) {
+      case opv::kEpiStore: return launch_gemm_tc<256, opv::kEpiStore>(tm_a, tm_b, ep, M, N, K, stream);
+      case opv::kEpiRope: return launch_gemm_tc<256, opv::kEpiRope>(tm_a, tm_b, ep, M, N, K, stream);
+      case opv::kEpiResidual: return launch_gemm_tc<256, opv::kEpiResidual>(tm_a, tm_b, ep, M, N, K, stream);
+      case opv::kEpiGeglu: return launch_gemm_tc<256, opv::kEpiGeglu>(tm_a, tm_b, ep, M, N, K, stream);
+    }
+  } else {
+    switch (epi) {
+      case opv::kEpiStore: return launch_gemm_tc<128, opv::kEpiStore>(tm_a, tm_b, ep, M, N, K, stream);
+      case opv::kEpiRope: return launch_gemm_tc<128, opv::kEpiRope>(tm_a, tm_b, ep, M, N, K, stream);
+      case opv::kEpiResidual: return launch_gemm_tc<128, opv::kEpiResidual>(tm_a, tm_b, ep, M, N, K, stream);
+    }
+  }
+  return fail(OPV_ERR_INVALID_ARGUMENT, "unknown epilogue %d", epi);
+}
+
+int gemm_f32(bool accumulate, const float* a, const float* w, float* c, int64_t M, int N, int K, int64_t ldc,
+             cudaStream_t stream) {
+  if (M <= 0) return OPV_OK;
+  if (N % 64 != 0 || K % 16 != 0) return fail(OPV_ERR_UNSUPPORTED, "fp32 GEMM needs N %% 64 == 0 and K %% 16 == 0");
+  dim3 grid(N / 64, static_cast<unsigned>((M + 63) / 64));
+  if (grid.y > 65535u) return fail(OPV_ERR_UNSUPPORTED, "fp32 GEMM: too many rows for one launch (%lld)", (long long)M);
+  if (accumulate)
+    opv::gemm_f32_simt_kernel<true><<<grid, 256, 0, stream>>>(a, w, c, (int)M, N, K, ldc);
+  else
+    opv::gemm_f32_simt_kernel<false><<<grid, 256, 0, stream>>>(a, w, c, (int)M, N, K, ldc);
+  OPV_LAUNCH_CHECK("gemm_f32_simt_kernel");
+  return OPV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-kernel dispatch on H / 128
+// ------------------------------------------------------------------------------------------------
+#define OPV_DISPATCH_VEC(H, ...)                                                       \
+  switch ((H) / 128) {                                                                 \
+    case 1: { constexpr int VEC = 1; __VA_ARGS__; } break;                             \
+    case 2: { constexpr int VEC = 2; __VA_ARGS__; } break;                             \
+    case 3: { constexpr int VEC = 3; __VA_ARGS__; } break;                             \
+    case 4: { constexpr int VEC = 4; __VA_ARGS__; } break;                             \
+    case 6: { constexpr int VEC = 6; __VA_ARGS__; } break;                             \
+    case 8: { constexpr int VEC = 8; __VA_ARGS__; } break;                             \
+    default: return fail(OPV_ERR_UNSUPPORTED, "hidden_size %d not in {128,256,384,512,768,1024}", (H)); \
+  }
+
+inline unsigned row_grid(int64_t M) { return static_cast<unsigned>((M + opv::kRowWarps - 1) / opv::kRowWarps); }
+
+template <typename OutT>
+int launch_layernorm(const float* h, const float* w, OutT* x, int64_t M, int H, float eps, cudaStream_t s) {
+  if (M <= 0) return OPV_OK;
+  OPV_DISPATCH_VEC(H, opv::layernorm_kernel<OutT, VEC><<<row_grid(M), opv::kRowWarps * 32, 0, s>>>(h, w, x, M, eps));
+  OPV_LAUNCH_CHECK("layernorm_kernel");
+  return OPV_OK;
+}
+
+template <typename EmbT, typename OutT>
+int launch_embed_ln(const int32_t* ids, const EmbT* emb, const float* w, float* h, OutT* x, int64_t M, int H, int V,
+                    float eps, cudaStream_t s) {
+  if (M <= 0) return OPV_OK;
+  OPV_DISPATCH_VEC(H, opv::embed_ln_kernel<EmbT, OutT, VEC>
+                       <<<row_grid(M), opv::kRowWarps * 32, 0, s>>>(ids, emb, w, h, x, M, V, eps));
+  OPV_LAUNCH_CHECK("embed_ln_kernel");
+  return OPV_OK;
+}
+
+int launch_final_prune(const float* h, const float* w, const float* wp, const float* bp, float* logits, int64_t M,
+                       int H, float eps, cudaStream_t s) {
+  if (M <= 0) return OPV_OK;
+  OPV_DISPATCH_VEC(H, opv::final_ln_prune_kernel<VEC>
+                       <<<row_grid(M), opv::kRowWarps * 32, 0, s>>>(h, w, wp, bp, logits, M, eps));
+  OPV_LAUNCH_CHECK("final_ln_prune_kernel");
+  return OPV_OK;
+}
+
+int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, int n_seqs, int max_seqlen, int heads,
+                     int half_window, cudaStream_t s) {
+  if (n_seqs <= 0 || max_seqlen <= 0) return OPV_OK;
+  if (n_seqs > 65535) return fail(OPV_ERR_UNSUPPORTED, "at most 65535 sequences per launch");
+  const int H = heads * 64;
+  if (dtype == OPV_DTYPE_BF16) {
+    dim3 grid((max_seqlen + opv::kAttBlockM - 1) / opv::kAttBlockM, heads, n_seqs);
+    opv::attention_mma_kernel<<<grid, opv::kAttThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv),
+                                                                static_cast<__nv_bfloat16*>(out), cu, H, half_window);
+    OPV_LAUNCH_CHECK("attention_mma_kernel");
+  } else {
+    dim3 grid((max_seqlen + 3) / 4, heads, n_seqs);
+    opv::attention_simt_kernel<float>
+        <<<grid, 128, 0, s>>>(static_cast<const float*>(qkv), static_cast<float*>(out), cu, H, half_window);
+    OPV_LAUNCH_CHECK("attention_simt_kernel");
+  }
+  return OPV_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------
+struct opv_engine {
+  opv_config cfg;
+  opv_weights w;
+  std::vector<opv_layer_weights> layers;
+  std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_wi, tm_wo2;  // bf16 mode only
+  int device;
+  size_t elt;  // bytes per operand element
+};
+
+struct WorkspaceLayout {
+  size_t h, x, qkv, attn, act, u, pos, total;
+};
+
+static WorkspaceLayout workspace_layout(const opv_engine* e, int64_t T) {
+  const size_t H = e->cfg.hidden_size, I = e->cfg.intermediate_size, elt = e->elt;
+  const bool unfused = e->cfg.dtype == OPV_DTYPE_F32 || !e->cfg.fuse_epilogues;
+  WorkspaceLayout l;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = off;
+    off += align_up(bytes, 1024);
+    return at;
+  };
+  const size_t rows = static_cast<size_t>(T > 0 ? T : 1);
+  l.h = take(rows * H * 4);
+  l.x = take(rows * H * elt);
+  l.qkv = take(rows * 3 * H * elt);
+  l.attn = take(rows * H * elt);
+  l.act = take(rows * I * elt);
+  l.u = take(unfused ? rows * 2 * I * elt : 0);
+  l.pos = take(rows * 4);
+  l.total = off;
+  return l;
+}
+
+extern "C" {
+
+const char* opv_last_error(void) { return g_last_error.c_str(); }
+int opv_abi_version(void) { return OPV_ABI_VERSION; }
+
+int opv_create(const opv_config* cfg, const opv_weights* w, int device, opv_handle* out) {
+  if (!cfg || !w || !out) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_create: null argument");
+  if (cfg->abi_version != OPV_ABI_VERSION)
+    return fail(OPV_ERR_INVALID_ARGUMENT, "ABI version mismatch: header %d, caller %d", OPV_ABI_VERSION,
+                cfg->abi_version);
+  if (cfg->num_layers <= 0 || cfg->num_layers > OPV_MAX_LAYERS)
+    return fail(OPV_ERR_UNSUPPORTED, "num_layers %d out of range", cfg->num_layers);
+  if (cfg->hidden_size != cfg->num_heads * 64)
+    return fail(OPV_ERR_UNSUPPORTED, "head_dim must be 64 (hidden_size %d, heads %d)", cfg->hidden_size,
+                cfg->num_heads);
+  if (cfg->hidden_size % 128 != 0 || cfg->hidden_size > 1024)
+    return fail(OPV_ERR_UNSUPPORTED, "hidden_size %d must be a multiple of 128 and <= 1024", cfg->hidden_size);
+  if (cfg->intermediate_size % 128 != 0)
+    return fail(OPV_ERR_UNSUPPORTED, "intermediate_size %d must be a multiple of 128", cfg->intermediate_size);
+  if (cfg->num_labels < 1) return fail(OPV_ERR_INVALID_ARGUMENT, "num_labels must be >= 1");
+  if (cfg->dtype != OPV_DTYPE_BF16 && cfg->dtype != OPV_DTYPE_F32)
+    return fail(OPV_ERR_INVALID_ARGUMENT, "unknown dtype %d", cfg->dtype);
+  if (!w->h_layers) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_create: weights.h_layers is null");
+  OPV_CUDA(cudaSetDevice(device));
+  if (int rc = ensure_device_setup()) return rc;
+
+  opv_engine* e = new opv_engine();
+  e->cfg = *cfg;
+  e->w = *w;
+  e->device = device;
+  e->elt = cfg->dtype == OPV_DTYPE_BF16 ? 2 : 4;
+  e->layers.assign(w->h_layers, w->h_layers + cfg->num_layers);
+  e->w.h_layers = e->layers.data();
+  const int H = cfg->hidden_size, I = cfg->intermediate_size;
+  for (int l = 0; l < cfg->num_layers; ++l) {
+    const opv_layer_weights& lw = e->layers[l];
+    if (!lw.d_wqkv || !lw.d_wo || !lw.d_wi || !lw.d_wo2 || !lw.d_mlp_norm || (l > 0 && !lw.d_attn_norm)) {
+      delete e;
+      return fail(OPV_ERR_INVALID_ARGUMENT, "layer %d: missing weight pointer", l);
+    }
+  }
+  if (cfg->dtype == OPV_DTYPE_BF16) {
+    e->tm_wqkv.resize(cfg->num_layers);
+    e->tm_wo.resize(cfg->num_layers);
+    e->tm_wi.resize(cfg->num_layers);
+    e->tm_wo2.resize(cfg->num_layers);
+    const bool fused = cfg->fuse_epilogues != 0;
+    for (int l = 0; l < cfg->num_layers; ++l) {
+      const opv_layer_weights& lw = e->layers[l];
+      int rc = 0;
+      const int bn_qkv = gemm_block_n(3 * H, fused ? opv::kEpiRope : opv::kEpiStore);
+      const int bn_h = gemm_block_n(H, opv::kEpiResidual);
+      const int bn_wi = gemm_block_n(2 * I, fused ? opv::kEpiGeglu : opv::kEpiStore);
+      if (!bn_qkv || !bn_h || !bn_wi) {
+        delete e;
+        return fail(OPV_ERR_UNSUPPORTED, "projection widths (3H=%d, H=%d, 2I=%d) do not tile", 3 * H, H, 2 * I);
+      }
+      rc = rc ? rc : make_tmap_bf16(&e->tm_wqkv[l], lw.d_wqkv, 3 * H, H, bn_qkv);
+      rc = rc ? rc : make_tmap_bf16(&e->tm_wo[l], lw.d_wo, H, H, bn_h);
+      rc = rc ? rc : make_tmap_bf16(&e->tm_wi[l], lw.d_wi, 2 * I, H, bn_wi);
+      rc = rc ? rc : make_tmap_bf16(&e->tm_wo2[l], lw.d_wo2, H, I, bn_h);
+      if (rc) {
+        delete e;
+        return rc;
+      }
+    }
+  }
+  *out = e;
+  return OPV_OK;
+}
+
+int opv_destroy(opv_handle h) {
+  delete h;
+  return OPV_OK;
+}
+
+size_t opv_workspace_bytes(opv_handle h, int64_t max_tokens, int32_t max_seqs) {
+  (void)max_seqs;
+  if (!h) return 0;
+  return workspace_layout(h, max_tokens).total + 1024;
+}
+
+int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_seqlens, int32_t n_seqs,
+                       int64_t n_tokens, int32_t max_seqlen, float* d_prune_logits, float* d_rank_logits,
+                       void* d_workspace, size_t workspace_bytes, void* stream_) {
+  if (!e) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_forward_packed: null engine");
+  if (n_seqs < 0 || n_tokens < 0) return fail(OPV_ERR_INVALID_ARGUMENT, "negative sizes");
+  if (n_seqs == 0 || n_tokens == 0) return OPV_OK;
+  if (!d_ids) return fail(OPV_ERR_INVALID_ARGUMENT, "input_ids must be provided");
+  if (!d_cu_seqlens || !d_prune_logits || !d_rank_logits || !d_workspace)
+    return fail(OPV_ERR_INVALID_ARGUMENT, "opv_forward_packed: null buffer");
+  if (max_seqlen <= 0 || max_seqlen > e->cfg.max_positions)
+    return fail(OPV_ERR_INVALID_ARGUMENT, "max_seqlen %d outside (0, max_positions=%d]", max_seqlen,
+                e->cfg.max_positions);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const opv_config& c = e->cfg;
+  const int H = c.hidden_size, I = c.intermediate_size, L = c.num_layers, heads = c.num_heads;
+  const int64_t T = n_tokens;
+  const WorkspaceLayout wl = workspace_layout(e, T);
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d_workspace) + 1023) & ~uintptr_t(1023));
+  if (static_cast<size_t>(ws - static_cast<uint8_t*>(d_workspace)) + wl.total > workspace_bytes)
+    return fail(OPV_ERR_WORKSPACE, "workspace too small: need %zu bytes, have %zu", wl.total + 1024, workspace_bytes);
+  float* h = reinterpret_cast<float*>(ws + wl.h);
+  void* x = ws + wl.x;
+  void* qkv = ws + wl.qkv;
+  void* attn = ws + wl.attn;
+  void* act = ws + wl.act;
+  void* u = ws + wl.u;
+  int32_t* pos = reinterpret_cast<int32_t*>(ws + wl.pos);
+  const int half_window = c.local_window / 2;
+
+  opv::positions_kernel<<<n_seqs, 256, 0, stream>>>(d_cu_seqlens, pos);
+  OPV_LAUNCH_CHECK("positions_kernel");
+
+  if (c.dtype == OPV_DTYPE_BF16) {
+    using bf16 = __nv_bfloat16;
+    const bool fused = c.fuse_epilogues != 0;
+    CUtensorMap tm_x, tm_attn, tm_act;
+    if (int rc = make_tmap_bf16(&tm_x, x, T, H, opv::kGemmBlockM)) return rc;
+    if (int rc = make_tmap_bf16(&tm_attn, attn, T, H, opv::kGemmBlockM)) return rc;
+    if (int rc = make_tmap_bf16(&tm_act, act, T, I, opv::kGemmBlockM)) return rc;
+    if (int rc = launch_embed_ln<bf16, bf16>(d_ids, static_cast<const bf16*>(e->w.d_tok_embeddings), e->w.d_emb_norm,
+                                             h, static_cast<bf16*>(x), T, H, c.vocab_size, c.norm_eps, stream))
+      return rc;
+    for (int l = 0; l < L; ++l) {
+      const opv_layer_weights& lw = e->layers[l];
+      const bool global = c.layer_is_global[l] != 0;
+      if (l > 0)
+        if (int rc = launch_layernorm<bf16>(h, lw.d_attn_norm, static_cast<bf16*>(x), T, H, c.norm_eps, stream))
+          return rc;
+      opv::GemmEpilogueArgs ep{};
+      ep.c = qkv, ep.ldc = 3 * H, ep.pos = pos, ep.rope_cols = 2 * H;
+      ep.cos = global ? e->w.d_rope_cos_global : e->w.d_rope_cos_local;
+      ep.sin = global ? e->w.d_rope_sin_global : e->w.d_rope_sin_local;
+      if (fused) {
+        if (int rc = gemm_bf16(opv::kEpiRope, tm_x, e->tm_wqkv[l], ep, T, 3 * H, H, stream)) return rc;
+      } else {
+        if (int rc = gemm_bf16(opv::kEpiStore, tm_x, e->tm_wqkv[l], ep, T, 3 * H, H, stream)) return rc;
+        opv::rope_inplace_kernel<bf16><<<g_num_sms * 8, 256, 0, stream>>>(static_cast<bf16*>(qkv), pos, ep.cos, ep.sin, T, H);
+        OPV_LAUNCH_CHECK("rope_inplace_kernel");
+      }
+      if (int rc = launch_attention(OPV_DTYPE_BF16, qkv, attn, d_cu_seqlens, n_seqs, max_seqlen, heads,
+                                    global ? -1 : half_window, stream))
+        return rc;
+      opv::GemmEpilogueArgs er{};
+      er.c = h, er.ldc = H;
+      if (int rc = gemm_bf16(opv::kEpiResidual, tm_attn, e->tm_wo[l], er, T, H, H, stream)) return rc;
+      if (int rc = launch_layernorm<bf16>(h, lw.d_mlp_norm, static_cast<bf16*>(x), T, H, c.norm_eps, stream)) return rc;
+      if (fused) {
+        opv::GemmEpilogueArgs eg{};
+        eg.c = act, eg.ldc = I;
+        if (int rc = gemm_bf16(opv::kEpiGeglu, tm_x, e->tm_wi[l], eg, T, 2 * I, H, stream)) return rc;
+      } else {
+        opv::GemmEpilogueArgs es{};
+        es.c = u, es.ldc = 2 * I;
+        if (int rc = gemm_bf16(opv::kEpiStore, tm_x, e->tm_wi[l], es, T, 2 * I, H, stream)) return rc;
+        opv::geglu_kernel<bf16><<<g_num_sms * 8, 256, 0, stream>>>(static_cast<const bf16*>(u), static_cast<bf16*>(act), T, I);
+        OPV_LAUNCH_CHECK("geglu_kernel");
+      }
+      if (int rc = gemm_bf16(opv::kEpiResidual, tm_act, e->tm_wo2[l], er, T, H, I, stream)) return rc;
+    }
+  } else {
+    float* xf = static_cast<float*>(x);
+    float* qf = static_cast<float*>(qkv);
+    float* af = static_cast<float*>(attn);
+    float* actf = static_cast<float*>(act);
+    float* uf = static_cast<float*>(u);
+    if (int rc = launch_embed_ln<float, float>(d_ids, static_cast<const float*>(e->w.d_tok_embeddings),
+                                               e->w.d_emb_norm, h, xf, T, H, c.vocab_size, c.norm_eps, stream))
+      return rc;
+    for (int l = 0; l < L; ++l) {
+      const opv_layer_weights& lw = e->layers[l];
+      const bool global = c.layer_is_global[l] != 0;
+      if (l > 0)
+        if (int rc = launch_layernorm<float>(h, lw.d_attn_norm, xf, T, H, c.norm_eps, stream)) return rc;
+      if (int rc = gemm_f32(false, xf, static_cast<const float*>(lw.d_wqkv), qf, T, 3 * H, H, 3 * H, stream)) return rc;
+      opv::rope_inplace_kernel<float><<<g_num_sms * 8, 256, 0, stream>>>(
+          qf, pos, global ? e->w.d_rope_cos_global : e->w.d_rope_cos_local,
+          global ? e->w.d_rope_sin_global : e->w.d_rope_sin_local, T, H);
+      OPV_LAUNCH_CHECK("rope_inplace_kernel");
+      if (int rc = launch_attention(OPV_DTYPE_F32, qf, af, d_cu_seqlens, n_seqs, max_seqlen, heads,
+                                    global ? -1 : half_window, stream))
+        return rc;
+      if (int rc = gemm_f32(true, af, static_cast<const float*>(lw.d_wo), h, T, H, H, H, stream)) return rc;
+      if (int rc = launch_layernorm<float>(h, lw.d_mlp_norm, xf, T, H, c.norm_eps, stream)) return rc;
+      if (int rc = gemm_f32(false, xf, static_cast<const float*>(lw.d_wi), uf, T, 2 * I, H, 2 * I, stream)) return rc;
+      opv::geglu_kernel<float><<<g_num_sms * 8, 256, 0, stream>>>(uf, actf, T, I);
+      OPV_LAUNCH_CHECK("geglu_kernel");
+      if (int rc = gemm_f32(true, actf, static_cast<const float*>(lw.d_wo2), h, T, H, I, H, stream)) return rc;
+    }
+  }
+
+  if (int rc = launch_final_prune(h, e->w.d_final_norm, e->w.d_prune_weight, e->w.d_prune_bias, d_prune_logits, T, H,
+                                  c.norm_eps, stream))
+    return rc;
+  opv::rank_head_kernel<<<n_seqs, 256, (2 * H + 8) * sizeof(float), stream>>>(
+      h, d_cu_seqlens, e->w.d_final_norm, e->w.d_head_dense, e->w.d_head_norm, e->w.d_cls_weight, e->w.d_cls_bias,
+      d_rank_logits, H, c.num_labels, c.norm_eps);
+  OPV_LAUNCH_CHECK("rank_head_kernel");
+  return OPV_OK;
+}
+
+int opv_fragment_means(const float* d_prune_logits, int64_t n_tokens, const int32_t* d_frag_ranges, int32_t n_frags,
+                       float* d_frag_mean, const float* d_rank_logits, int32_t n_seqs, int32_t num_labels,
+                       float* d_rank_score, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_frags > 0) {
+    if (!d_prune_logits || !d_frag_ranges || !d_frag_mean)
+      return fail(OPV_ERR_INVALID_ARGUMENT, "opv_fragment_means: null buffer");
+    opv::fragment_mean_kernel<<<(n_frags + opv::kRowWarps - 1) / opv::kRowWarps, opv::kRowWarps * 32, 0, stream>>>(
+        d_prune_logits, n_tokens, d_frag_ranges, n_frags, d_frag_mean);
+    OPV_LAUNCH_CHECK("fragment_mean_kernel");
+  }
+  if (n_seqs > 0 && d_rank_score) {
+    if (!d_rank_logits || num_labels < 1) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_fragment_means: rank logits");
+    opv::rank_score_kernel<<<(n_seqs + 255) / 256, 256, 0, stream>>>(d_rank_logits, n_seqs, num_labels, d_rank_score);
+    OPV_LAUNCH_CHECK("rank_score_kernel");
+  }
+  return OPV_OK;
+}
+
+int opv_sentence_prune(const float* d_frag_mean, const int32_t* d_sent_offsets, const int32_t* d_sent_frag_index,
+                       int32_t n_sents, double threshold, double guard, double* d_sent_prob, uint8_t* d_keep,
+                       uint8_t* d_near, void* stream_) {
+  if (n_sents <= 0) return OPV_OK;
+  if (!d_frag_mean || !d_sent_offsets || !d_sent_frag_index || !d_sent_prob || !d_keep || !d_near)
+    return fail(OPV_ERR_INVALID_ARGUMENT, "opv_sentence_prune: null buffer");
+  opv::sentence_prune_kernel<<<(n_sents + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      d_frag_mean, d_sent_offsets, d_sent_frag_index, n_sents, threshold, guard, d_sent_prob, d_keep, d_near);
+  OPV_LAUNCH_CHECK("sentence_prune_kernel");
+  return OPV_OK;
+}
+
+// ---- single-op entry points -----------------------------------------------------------------------
+
+int opv_op_gemm(int32_t dtype, int32_t epilogue, const void* d_a, const void* d_w, void* d_c, int64_t m, int32_t n,
+                int32_t k, const int32_t* d_pos, const float* d_cos, const float* d_sin, int32_t hidden_size,
+                void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d_a || !d_w || !d_c) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_op_gemm: null buffer");
+  if (int rc = ensure_device_setup()) return rc;
+  if (dtype == OPV_DTYPE_F32) {
+    if (epilogue == OPV_EPI_STORE)
+      return gemm_f32(false, static_cast<const float*>(d_a), static_cast<const float*>(d_w), static_cast<float*>(d_c),
+                      m, n, k, n, stream);
+    if (epilogue == OPV_EPI_RESIDUAL)
+      return gemm_f32(true, static_cast<const float*>(d_a), static_cast<const float*>(d_w), static_cast<float*>(d_c),
+                      m, n, k, n, stream);
+    return fail(OPV_ERR_UNSUPPORTED, "fp32 GEMM has STORE and RESIDUAL epilogues only");
+  }
+  if (m <= 0) return OPV_OK;
+  const int bn = gemm_block_n(n, epilogue);
+  if (bn == 0) return fail(OPV_ERR_UNSUPPORTED, "N = %d does not tile for epilogue %d", n, epilogue);
+  CUtensorMap tm_a, tm_b;
+  if (int rc = make_tmap_bf16(&tm_a, d_a, m, k, opv::kGemmBlockM)) return rc;
+  if (int rc = make_tmap_bf16(&tm_b, d_w, n, k, bn)) return rc;
+  opv::GemmEpilogueArgs ep{};
+  ep.c = d_c;
+  ep.ldc = (epilogue == OPV_EPI_GEGLU) ? n / 2 : n;
+  ep.pos = d_pos, ep.cos = d_cos, ep.sin = d_sin, ep.rope_cols = 2 * hidden_size;
+  if (epilogue == OPV_EPI_ROPE && (!d_pos || !d_cos || !d_sin || n != 3 * hidden_size))
+    return fail(OPV_ERR_INVALID_ARGUMENT, "ROPE epilogue needs pos/cos/sin and N == 3 * hidden_size");
+  return gemm_bf16(epilogue, tm_a, tm_b, ep, m, n, k, stream);
+}
+
+int opv_op_layernorm(int32_t dtype, const float* d_h, const float* d_w, void* d_out, int64_t m, int32_t hidden,
+                     float eps, void* stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (dtype == OPV_DTYPE_BF16) return launch_layernorm<__nv_bfloat16>(d_h, d_w, static_cast<__nv_bfloat16*>(d_out), m, hidden, eps, s);
+  return launch_layernorm<float>(d_h, d_w, static_cast<float*>(d_out), m, hidden, eps, s);
+}
+
+int opv_op_embed_ln(int32_t dtype, const int32_t* d_ids, const void* d_emb, const float* d_w, float* d_h, void* d_x,
+                    int64_t m, int32_t hidden, int32_t vocab, float eps, void* stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (dtype == OPV_DTYPE_BF16)
+    return launch_embed_ln<__nv_bfloat16, __nv_bfloat16>(d_ids, static_cast<const __nv_bfloat16*>(d_emb), d_w, d_h,
+                                                         static_cast<__nv_bfloat16*>(d_x), m, hidden, vocab, eps, s);
+  return launch_embed_ln<float, float>(d_ids, static_cast<const float*>(d_emb), d_w, d_h, static_cast<float*>(d_x), m,
+                                       hidden, vocab, eps, s);
+}
+
+int opv_op_attention(int32_t dtype, const void* d_qkv, void* d_out, const int32_t* d_cu_seqlens, int32_t n_seqs,
+                     int32_t max_seqlen, int32_t num_heads, int32_t half_window, void* stream_) {
+  return launch_attention(dtype, d_qkv, d_out, d_cu_seqlens, n_seqs, max_seqlen, num_heads, half_window,
+                          static_cast<cudaStream_t>(stream_));
+}
+
+int opv_op_rope(int32_t dtype, void* d_qkv, const int32_t* d_pos, const float* d_cos, const float* d_sin, int64_t m,
+                int32_t hidden, void* stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (m <= 0) return OPV_OK;
+  if (dtype == OPV_DTYPE_BF16)
+    opv::rope_inplace_kernel<__nv_bfloat16><<<1184, 256, 0, s>>>(static_cast<__nv_bfloat16*>(d_qkv), d_pos, d_cos, d_sin, m, hidden);
+  else
+    opv::rope_inplace_kernel<float><<<1184, 256, 0, s>>>(static_cast<float*>(d_qkv), d_pos, d_cos, d_sin, m, hidden);
+  OPV_LAUNCH_CHECK("rope_inplace_kernel");
+  return OPV_OK;
+}
+
+int opv_op_geglu(int32_t dtype, const void* d_u, void* d_act, int64_t m, int32_t intermediate, void* stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (m <= 0) return OPV_OK;
+  if (dtype == OPV_DTYPE_BF16)
+    opv::geglu_kernel<__nv_bfloat16><<<1184, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(d_u), static_cast<__nv_bfloat16*>(d_act), m, intermediate);
+  else
+    opv::geglu_kernel<float><<<1184, 256, 0, s>>>(static_cast<const float*>(d_u), static_cast<float*>(d_act), m, intermediate);
+  OPV_LAUNCH_CHECK("geglu_kernel");
+  return OPV_OK;
+}
+
+int opv_op_positions(const int32_t* d_cu_seqlens, int32_t n_seqs, int32_t* d_pos, void* stream_) {
+  if (n_seqs <= 0) return OPV_OK;
+  opv::positions_kernel<<<n_seqs, 256, 0, static_cast<cudaStream_t>(stream_)>>>(d_cu_seqlens, d_pos);
+  OPV_LAUNCH_CHECK("positions_kernel");
+  return OPV_OK;
+}
+
+}  // extern "C"

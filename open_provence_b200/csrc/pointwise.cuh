@@ -1,0 +1,315 @@
+// HBM-bound row kernels: embedding gather + LayerNorm, LayerNorm, final LayerNorm fused with the
+// token-mask (pruning) head, the CLS rerank head, unfused RoPE / GeGLU (fp32 parity mode and the
+// unfused bf16 debug path), positions, and the score-conversion / per-sentence prune kernels.
+// One warp owns one token row; rows are read once with 16 B loads and written once.
+#pragma once
+
+#include "common.cuh"
+
+namespace opv {
+
+constexpr int kRowWarps = 8;  // warps (rows) per CTA for the row kernels
+
+// ---------------------------------------------------------------------------------------------
+// row load / store helpers (VEC float4 per lane, H = VEC * 128)
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__device__ __forceinline__ void load_row_f32(const float* __restrict__ src, int lane, float4 (&v)[VEC]) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) v[i] = *reinterpret_cast<const float4*>(src + (i * 32 + lane) * 4);
+}
+template <int VEC>
+__device__ __forceinline__ void load_row_bf16(const __nv_bfloat16* __restrict__ src, int lane, float4 (&v)[VEC]) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const uint2 u = *reinterpret_cast<const uint2*>(src + (i * 32 + lane) * 4);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    v[i] = make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+  }
+}
+__device__ __forceinline__ void store4(float* dst, float4 v) { *reinterpret_cast<float4*>(dst) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* dst, float4 v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(dst) = u;
+}
+
+// LayerNorm statistics over one row held by a warp (nn.LayerNorm: biased variance, HF:60,321,323,432).
+template <int VEC>
+__device__ __forceinline__ void row_norm_stats(const float4 (&v)[VEC], float eps, float& mean, float& rstd) {
+  constexpr float inv_h = 1.0f / static_cast<float>(VEC * 128);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  mean = warp_sum(s) * inv_h;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  rstd = 1.0f / sqrtf(warp_sum(q) * inv_h + eps);
+}
+template <int VEC>
+__device__ __forceinline__ void row_normalize(float4 (&v)[VEC], const float* __restrict__ w, int lane, float mean,
+                                              float rstd) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w + (i * 32 + lane) * 4));
+    v[i].x = (v[i].x - mean) * rstd * g.x;
+    v[i].y = (v[i].y - mean) * rstd * g.y;
+    v[i].z = (v[i].z - mean) * rstd * g.z;
+    v[i].w = (v[i].w - mean) * rstd * g.w;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: h = LN(E[ids]) (fp32 residual stream), x = cast(h) (layer 0 has no attn_norm, HF:318-319)
+// ---------------------------------------------------------------------------------------------
+template <typename EmbT, typename OutT, int VEC>
+__global__ void __launch_bounds__(kRowWarps * 32)
+embed_ln_kernel(const int32_t* __restrict__ ids, const EmbT* __restrict__ emb, const float* __restrict__ w,
+                float* __restrict__ h, OutT* __restrict__ x, const int64_t M, const int vocab, const float eps) {
+  constexpr int H = VEC * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  if (row >= M) return;
+  int id = ids[row];
+  id = min(max(id, 0), vocab - 1);  // ids are validated on the host; never read out of bounds
+  float4 v[VEC];
+  if constexpr (sizeof(EmbT) == 2) {
+    load_row_bf16<VEC>(reinterpret_cast<const __nv_bfloat16*>(emb) + static_cast<int64_t>(id) * H, lane, v);
+  } else {
+    load_row_f32<VEC>(reinterpret_cast<const float*>(emb) + static_cast<int64_t>(id) * H, lane, v);
+  }
+  float mean, rstd;
+  row_norm_stats<VEC>(v, eps, mean, rstd);
+  row_normalize<VEC>(v, w, lane, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    store4(h + row * H + (i * 32 + lane) * 4, v[i]);
+    store4(x + row * H + (i * 32 + lane) * 4, v[i]);
+  }
+}
+
+// K2/K8: x = LN(h) * w
+template <typename OutT, int VEC>
+__global__ void __launch_bounds__(kRowWarps * 32)
+layernorm_kernel(const float* __restrict__ h, const float* __restrict__ w, OutT* __restrict__ x, const int64_t M,
+                 const float eps) {
+  constexpr int H = VEC * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float4 v[VEC];
+  load_row_f32<VEC>(h + row * H, lane, v);
+  float mean, rstd;
+  row_norm_stats<VEC>(v, eps, mean, rstd);
+  row_normalize<VEC>(v, w, lane, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) store4(x + row * H + (i * 32 + lane) * 4, v[i]);
+}
+
+// K11 + K12: prune_logits[t] = LN(h[t]; final_norm) . Wp^T + bp  (HF:488 + standalone:446-447).
+// The final hidden state is never written to HBM.
+template <int VEC>
+__global__ void __launch_bounds__(kRowWarps * 32)
+final_ln_prune_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ wp,
+                      const float* __restrict__ bp, float* __restrict__ logits, const int64_t M, const float eps) {
+  constexpr int H = VEC * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float4 v[VEC];
+  load_row_f32<VEC>(h + row * H, lane, v);
+  float mean, rstd;
+  row_norm_stats<VEC>(v, eps, mean, rstd);
+  row_normalize<VEC>(v, w, lane, mean, rstd);
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(wp + (i * 32 + lane) * 4));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(wp + H + (i * 32 + lane) * 4));
+    d0 += v[i].x * a.x + v[i].y * a.y + v[i].z * a.z + v[i].w * a.w;
+    d1 += v[i].x * b.x + v[i].y * b.y + v[i].z * b.z + v[i].w * b.w;
+  }
+  d0 = warp_sum(d0);
+  d1 = warp_sum(d1);
+  if (lane == 0) {
+    logits[row * 2 + 0] = d0 + bp[0];
+    logits[row * 2 + 1] = d1 + bp[1];
+  }
+}
+
+// K13: rank_logits[s] = classifier(LN(gelu(dense(LN(h[cls_s]; final_norm))); head.norm)) (HF:621-634,493-502)
+// One CTA per sequence; "cls" pooling only.
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i];
+  return t;
+}
+__global__ void __launch_bounds__(256)
+rank_head_kernel(const float* __restrict__ h, const int32_t* __restrict__ cu_seqlens,
+                 const float* __restrict__ final_norm, const float* __restrict__ dense,
+                 const float* __restrict__ head_norm, const float* __restrict__ cls_w,
+                 const float* __restrict__ cls_b, float* __restrict__ rank_logits, const int H, const int num_labels,
+                 const float eps) {
+  extern __shared__ float sm[];
+  float* cls = sm;        // [H]
+  float* y = sm + H;      // [H]
+  float* red = sm + 2 * H;  // [8]
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = h + static_cast<int64_t>(cu_seqlens[s]) * H;
+  const float inv_h = 1.0f / static_cast<float>(H);
+
+  float part = 0.f;
+  for (int i = tid; i < H; i += 256) part += row[i];
+  const float mean = block_sum_256(part, red) * inv_h;
+  part = 0.f;
+  for (int i = tid; i < H; i += 256) {
+    const float d = row[i] - mean;
+    part += d * d;
+  }
+  const float rstd = 1.0f / sqrtf(block_sum_256(part, red) * inv_h + eps);
+  for (int i = tid; i < H; i += 256) cls[i] = (row[i] - mean) * rstd * final_norm[i];
+  __syncthreads();
+
+  for (int j = warp; j < H; j += 8) {  // dense has no bias (classifier_bias = False)
+    const float* wr = dense + static_cast<int64_t>(j) * H;
+    float acc = 0.f;
+    for (int i = lane; i < H; i += 32) acc = fmaf(cls[i], wr[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[j] = gelu_erf(acc);
+  }
+  __syncthreads();
+
+  part = 0.f;
+  for (int i = tid; i < H; i += 256) part += y[i];
+  const float mean2 = block_sum_256(part, red) * inv_h;
+  part = 0.f;
+  for (int i = tid; i < H; i += 256) {
+    const float d = y[i] - mean2;
+    part += d * d;
+  }
+  const float rstd2 = 1.0f / sqrtf(block_sum_256(part, red) * inv_h + eps);
+  __syncthreads();
+  for (int i = tid; i < H; i += 256) y[i] = (y[i] - mean2) * rstd2 * head_norm[i];
+  __syncthreads();
+
+  for (int l = warp; l < num_labels; l += 8) {
+    const float* wr = cls_w + static_cast<int64_t>(l) * H;
+    float acc = 0.f;
+    for (int i = lane; i < H; i += 32) acc = fmaf(y[i], wr[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) rank_logits[static_cast<int64_t>(s) * num_labels + l] = acc + cls_b[l];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// positions: pos[t] = t - cu_seqlens[seq(t)]  (RoPE restarts at 0 for every packed sequence)
+// ---------------------------------------------------------------------------------------------
+__global__ void positions_kernel(const int32_t* __restrict__ cu_seqlens, int32_t* __restrict__ pos) {
+  const int s = blockIdx.x;
+  const int begin = cu_seqlens[s], end = cu_seqlens[s + 1];
+  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) pos[i] = i - begin;
+}
+
+// ---------------------------------------------------------------------------------------------
+// unfused RoPE (in place on the q,k thirds of qkv [M, 3H]) and GeGLU -- fp32 parity mode
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void rope_inplace_kernel(T* __restrict__ qkv, const int32_t* __restrict__ pos,
+                                    const float* __restrict__ cos_t, const float* __restrict__ sin_t, const int64_t M,
+                                    const int H) {
+  const int heads2 = 2 * (H / 64);  // q heads then k heads: contiguous first 2H columns
+  const int64_t total = M * heads2 * 32;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx & 31);
+    const int64_t rh = idx >> 5;
+    const int hd = static_cast<int>(rh % heads2);
+    const int64_t row = rh / heads2;
+    const int p = pos[row];
+    const float c = cos_t[static_cast<int64_t>(p) * 32 + i], s = sin_t[static_cast<int64_t>(p) * 32 + i];
+    T* base = qkv + row * (3 * static_cast<int64_t>(H)) + hd * 64;
+    const float a = OperandCast<T>::to_float(base[i]), b = OperandCast<T>::to_float(base[i + 32]);
+    base[i] = OperandCast<T>::from_float(a * c - b * s);
+    base[i + 32] = OperandCast<T>::from_float(b * c + a * s);
+  }
+}
+
+template <typename T>
+__global__ void geglu_kernel(const T* __restrict__ u, T* __restrict__ act, const int64_t M, const int I) {
+  const int64_t total = M * I;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = idx / I;
+    const int j = static_cast<int>(idx - row * I);
+    const float a = OperandCast<T>::to_float(u[row * 2 * I + j]);
+    const float g = OperandCast<T>::to_float(u[row * 2 * I + I + j]);
+    act[idx] = OperandCast<T>::from_float(gelu_erf(a) * g);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K14 + K15: score conversion and the per-sentence threshold / prune
+// ---------------------------------------------------------------------------------------------
+// keep-prob of a token = softmax(l)[1] evaluated like the reference's fp32 softmax (standalone:2918)
+__device__ __forceinline__ float keep_prob(float l0, float l1) {
+  const float m = fmaxf(l0, l1);
+  const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+  return e1 / (e0 + e1);
+}
+
+// one warp per fragment: coalesced read of the fragment's [start, end) logits, warp-shuffle sum
+__global__ void __launch_bounds__(kRowWarps * 32)
+fragment_mean_kernel(const float* __restrict__ logits, const int64_t n_tokens, const int32_t* __restrict__ ranges,
+                     const int n_frags, float* __restrict__ frag_mean) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (f >= n_frags) return;
+  int64_t start = ranges[2 * f], end = ranges[2 * f + 1];
+  start = max(static_cast<int64_t>(0), min(start, n_tokens));
+  end = max(start, min(end, n_tokens));
+  float s = 0.f;
+  const float2* l2 = reinterpret_cast<const float2*>(logits);
+  for (int64_t t = start + lane; t < end; t += 32) {
+    const float2 l = __ldg(l2 + t);
+    s += keep_prob(l.x, l.y);
+  }
+  s = warp_sum(s);
+  if (lane == 0) frag_mean[f] = (end <= start) ? 1.0f : s / static_cast<float>(end - start);  // standalone:3081
+}
+
+__global__ void rank_score_kernel(const float* __restrict__ rank_logits, const int n_seqs, const int num_labels,
+                                  float* __restrict__ score) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_seqs) score[s] = 1.0f / (1.0f + expf(-rank_logits[static_cast<int64_t>(s) * num_labels]));
+}
+
+// one thread per sentence: unweighted fp64 mean of its fragment means (standalone:3116-3134)
+__global__ void sentence_prune_kernel(const float* __restrict__ frag_mean, const int32_t* __restrict__ sent_offsets,
+                                      const int32_t* __restrict__ sent_frag_index, const int n_sents,
+                                      const double threshold, const double guard, double* __restrict__ sent_prob,
+                                      uint8_t* __restrict__ keep, uint8_t* __restrict__ near) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sents) return;
+  const int b = sent_offsets[s], e = sent_offsets[s + 1];
+  double acc = 0.0;
+  for (int k = b; k < e; ++k) acc += static_cast<double>(frag_mean[sent_frag_index[k]]);
+  double p = (e > b) ? acc / static_cast<double>(e - b) : 0.0;
+  p = fmax(0.0, fmin(p, 1.0));
+  sent_prob[s] = p;
+  keep[s] = p > threshold ? 1 : 0;
+  near[s] = fabs(p - threshold) <= guard ? 1 : 0;
+}
+
+}  // namespace opv

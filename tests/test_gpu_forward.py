@@ -1,0 +1,77 @@
+"""Engine forward (through the C ABI) against the golden fixtures produced by the reference itself."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from open_provence_b200.engine import Engine  # noqa: E402
+
+DEV = "cuda"
+
+
+def _state_dict(tiny_ckpt_dir):
+    from safetensors.torch import load_file
+
+    return load_file(str(tiny_ckpt_dir / "model.safetensors"))
+
+
+def _pack(golden):
+    lengths = golden["lengths"].tolist()
+    ids = np.concatenate([golden["input_ids"][b, :n] for b, n in enumerate(lengths)]).astype(np.int32)
+    cu = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int32)
+    return torch.from_numpy(ids).to(DEV), torch.from_numpy(cu).to(DEV), lengths
+
+
+def _errors(prune, rank, golden, lengths, key):
+    ref_rank = golden[f"ranking_logits_{key}"]
+    ref_prune = np.concatenate([golden[f"pruning_logits_{key}"][b, :n] for b, n in enumerate(lengths)])
+    e_rank = np.abs(rank.cpu().double().numpy() - ref_rank).max()
+    e_prune = np.abs(prune.cpu().double().numpy() - ref_prune).max()
+    return e_rank, e_prune, np.abs(ref_prune).max()
+
+
+def test_forward_fp32_matches_reference_1e5(tiny_ckpt_dir, tiny_config, forward_golden):
+    eng = Engine(tiny_config["base_model_config"], _state_dict(tiny_ckpt_dir), device=DEV, dtype="fp32",
+                 num_labels=tiny_config["num_labels"])
+    ids, cu, lengths = _pack(forward_golden)
+    prune, rank = eng.forward_packed(ids, cu, max(lengths))
+    torch.cuda.synchronize()
+    e_rank, e_prune, scale = _errors(prune, rank, forward_golden, lengths, "f64")
+    print(f"fp32 engine vs fp64 reference: rank {e_rank:.3e} prune {e_prune:.3e} (|prune| max {scale:.2f})")
+    # north_star tolerance for the fp32 mode: 1e-5 (the reference's own fp32 forward is 6e-6 off fp64 here)
+    assert e_rank < 1e-5 and e_prune < 1e-5
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_forward_bf16_matches_reference(tiny_ckpt_dir, tiny_config, forward_golden, fused):
+    eng = Engine(tiny_config["base_model_config"], _state_dict(tiny_ckpt_dir), device=DEV, dtype="bf16",
+                 num_labels=tiny_config["num_labels"], fuse_epilogues=fused)
+    ids, cu, lengths = _pack(forward_golden)
+    prune, rank = eng.forward_packed(ids, cu, max(lengths))
+    torch.cuda.synchronize()
+    e_rank, e_prune, scale = _errors(prune, rank, forward_golden, lengths, "f64")
+    print(f"bf16 engine (fused={fused}) vs fp64 reference: rank {e_rank:.3e} prune {e_prune:.3e} (|prune| max {scale:.2f})")
+    assert torch.isfinite(prune).all() and torch.isfinite(rank).all()
+    # bf16 operands (8-bit mantissa) through 4 layers; logits here reach |l| ~ 10 (prune head sigma 0.3)
+    assert e_rank < 2e-2 and e_prune < 1e-1
+
+
+def test_forward_is_deterministic_and_batch_invariant(tiny_ckpt_dir, tiny_config, forward_golden):
+    """Packing more sequences into the launch must not change any sequence's result (unpadded packing)."""
+    eng = Engine(tiny_config["base_model_config"], _state_dict(tiny_ckpt_dir), device=DEV, dtype="bf16",
+                 num_labels=tiny_config["num_labels"])
+    ids, cu, lengths = _pack(forward_golden)
+    prune_all, rank_all = eng.forward_packed(ids, cu, max(lengths))
+    prune_again, rank_again = eng.forward_packed(ids, cu, max(lengths))
+    b = len(lengths) - 1
+    lo, hi = int(cu[b]), int(cu[b + 1])
+    one_cu = torch.tensor([0, hi - lo], dtype=torch.int32, device=DEV)
+    prune_one, rank_one = eng.forward_packed(ids[lo:hi].contiguous(), one_cu, hi - lo)
+    torch.cuda.synchronize()
+    assert torch.equal(prune_all, prune_again) and torch.equal(rank_all, rank_again)
+    assert torch.equal(prune_all[lo:hi], prune_one)
+    assert torch.equal(rank_all[b : b + 1], rank_one)
