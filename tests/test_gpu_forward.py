@@ -36,7 +36,7 @@ def _errors(prune, rank, golden, lengths, key):
 
 def test_forward_fp32_matches_reference_1e5(tiny_ckpt_dir, tiny_config, forward_golden):
     eng = Engine(tiny_config["base_model_config"], _state_dict(tiny_ckpt_dir), device=DEV, dtype="fp32",
-                 num_labels=tiny_config["num_labels"])
+                 num_labels=len(tiny_config.get("id2label") or {0: 0}))
     ids, cu, lengths = _pack(forward_golden)
     prune, rank = eng.forward_packed(ids, cu, max(lengths))
     torch.cuda.synchronize()
@@ -49,7 +49,7 @@ def test_forward_fp32_matches_reference_1e5(tiny_ckpt_dir, tiny_config, forward_
 @pytest.mark.parametrize("fused", [True, False])
 def test_forward_bf16_matches_reference(tiny_ckpt_dir, tiny_config, forward_golden, fused):
     eng = Engine(tiny_config["base_model_config"], _state_dict(tiny_ckpt_dir), device=DEV, dtype="bf16",
-                 num_labels=tiny_config["num_labels"], fuse_epilogues=fused)
+                 num_labels=len(tiny_config.get("id2label") or {0: 0}), fuse_epilogues=fused)
     ids, cu, lengths = _pack(forward_golden)
     prune, rank = eng.forward_packed(ids, cu, max(lengths))
     torch.cuda.synchronize()
@@ -63,7 +63,7 @@ def test_forward_bf16_matches_reference(tiny_ckpt_dir, tiny_config, forward_gold
 def test_forward_is_deterministic_and_batch_invariant(tiny_ckpt_dir, tiny_config, forward_golden):
     """Packing more sequences into the launch must not change any sequence's result (unpadded packing)."""
     eng = Engine(tiny_config["base_model_config"], _state_dict(tiny_ckpt_dir), device=DEV, dtype="bf16",
-                 num_labels=tiny_config["num_labels"])
+                 num_labels=len(tiny_config.get("id2label") or {0: 0}))
     ids, cu, lengths = _pack(forward_golden)
     prune_all, rank_all = eng.forward_packed(ids, cu, max(lengths))
     prune_again, rank_again = eng.forward_packed(ids, cu, max(lengths))
