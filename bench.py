@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the OpenProvence scoring-and-pruning hot path on B200 (contract: see DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic pre-tokenised (question, context)
+blocks: ModernBERT forward -> rerank score + token keep-probabilities -> per-sentence mean /
+threshold / prune.  Metric: query-context pairs/sec at seq_len=2048, base-130M (BASELINE.json).
+Weak scaling: every GPU gets its own batch of 64 blocks; for N > 1 each step ends with the single
+NCCL all-gather of the per-block scores and per-sentence results.
+
+Rank 0 prints ONE JSON line.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "query-context pairs/sec at seq_len=2048, base-130M"
+UNIT = "pairs/s"
+THRESHOLD = 0.1
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="base-130M")
+    ap.add_argument("--seq-len", type=int, default=2048)
+    ap.add_argument("--batch", type=int, default=64, help="blocks per GPU per step")
+    ap.add_argument("--mode", default="dense", choices=["dense", "ragged"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-pairs", type=int, default=4, help="pairs in the bounded CPU-baseline sample")
+    ap.add_argument("--ref-pairs-per-step", type=int, default=2)
+    return ap.parse_args()
+
+
+def measured_peaks() -> dict:
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        data = json.loads(path.read_text())
+        data["source"] = "measured"
+        return data
+    # B200_PROFILING.md fallback (an earlier measurement on this pool)
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    FIELDS = (
+        "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+        "clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower() == "active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {
+            "sm_mhz": statistics.median(sm),
+            "sm_max_mhz": max(smax),
+            "power_w_max": max(power),
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def dist_setup(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def run_reference(args, world: int, rank: int) -> None:
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    from open_provence_b200 import synthetic as syn
+    from oracle import hf_cpu_baseline as hb
+
+    cfg = syn.backbone_config(args.model)
+    sd = syn.random_state_dict(cfg, seed=0)
+    model, head = hb.build_hf_model(cfg, sd)
+    per_step = max(1, args.ref_pairs_per_step)
+    n_pairs = per_step * (args.steps + args.warmup)
+    wl = syn.make_workload(cfg, n_pairs, args.seq_len, mode=args.mode, seed=1234)
+    at = 0
+    for _ in range(args.warmup):
+        hb.score_workload(model, head, wl, slice(at, at + per_step), THRESHOLD)
+        at += per_step
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hb.score_workload(model, head, wl, slice(at, at + per_step), THRESHOLD)
+        at += per_step
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = f"{per_step} blocks of {args.seq_len} tokens per step, {args.steps} steps, HF ModernBERT fp32 sdpa on CPU"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.model} seq_len={args.seq_len} {args.mode}, {per_step} blocks per step (bounded CPU sample)",
+                   "transformers": __import__("transformers").__version__},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    args = parse_args()
+    world, rank, local = dist_setup(args)
+    if args.impl == "reference":
+        run_reference(args, world, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback)")
+    from open_provence_b200 import synthetic as syn
+    from open_provence_b200.engine import Engine
+    from oracle.modernbert_numpy import algorithmic_flops_per_pair
+
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    cfg = syn.backbone_config(args.model)
+    sd = syn.random_state_dict(cfg, seed=0)
+    eng = Engine(cfg, sd, device=dev, dtype=args.dtype, num_labels=1)
+    del sd
+    wl = syn.make_workload(cfg, args.batch, args.seq_len, mode=args.mode, seed=1234 + rank)
+    T = int(wl["ids"].shape[0])
+    n_frags = int(wl["frag_ranges"].shape[0])
+
+    # host (pinned) and device-resident copies of the step inputs
+    host = {k: torch.from_numpy(wl[k]).pin_memory() for k in ("ids", "cu_seqlens", "frag_ranges", "sent_offsets", "sent_frag_index")}
+    d = {k: v.to(dev) for k, v in host.items()}
+
+    frag_max = n_frags
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([n_frags], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        frag_max = int(t.item())
+    rec_len = args.batch + 2 * frag_max
+    record = torch.zeros(rec_len, dtype=torch.float32, device=dev)
+    gathered = torch.empty(world * rec_len, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step_device():
+        prune, rank_logits = eng.forward_packed(d["ids"], d["cu_seqlens"], wl["max_seqlen"])
+        frag_mean, score = eng.fragment_means(prune, d["frag_ranges"], rank_logits)
+        prob, keep, near = eng.sentence_prune(frag_mean, d["sent_offsets"], d["sent_frag_index"], THRESHOLD)
+        if world > 1:
+            record[: args.batch] = score
+            record[args.batch : args.batch + n_frags] = prob.float()
+            record[args.batch + frag_max : args.batch + frag_max + n_frags] = keep.float()
+            dist.all_gather_into_tensor(gathered, record)
+        return score, prob, keep
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    sync_all()
+    launches_before = eng.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    sync_all()
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    # forward launches (counted in the engine) + 3 prune-path kernels per step
+    launches = (eng.launch_count() - launches_before) // args.steps + 3
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * args.batch / (ms_per_step * 1e-3)
+
+    # ---- e2e: the host-buffer call, H2D of the step's inputs and D2H of its results inside the timed region
+    h2d = sum(int(v.numel() * v.element_size()) for v in host.values())
+    for _ in range(2):
+        out = eng.score_packed_host(host["ids"], host["cu_seqlens"], wl["max_seqlen"], host["frag_ranges"],
+                                    host["sent_offsets"], host["sent_frag_index"], THRESHOLD)
+    d2h = sum(int(v.numel() * v.element_size()) for v in out.values())
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = eng.score_packed_host(host["ids"], host["cu_seqlens"], wl["max_seqlen"], host["frag_ranges"],
+                                    host["sent_offsets"], host["sent_frag_index"], THRESHOLD)
+        if world > 1:
+            record[: args.batch] = out["rank_score"].to(dev, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, record)
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * args.batch * args.steps / e2e_s
+
+    # ---- per-kernel-class device times of one step (CUDA events on the launch stream, inside the library)
+    eng.profile(True)
+    prof_steps = min(3, args.steps)
+    for _ in range(prof_steps):
+        eng.forward_packed(d["ids"], d["cu_seqlens"], wl["max_seqlen"])
+    prof = eng.profile_collect()
+    eng.profile(False)
+    profile_ms = {k: round(v["ms"] / prof_steps, 4) for k, v in prof.items()}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    H, I, L = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_hidden_layers"]
+    gemm_flops = {
+        "gemm_qkv_rope": 2.0 * T * 3 * H * H,
+        "gemm_wo_residual": 2.0 * T * H * H,
+        "gemm_wi_geglu": 2.0 * T * 2 * I * H,
+        "gemm_wo2_residual": 2.0 * T * H * I,
+    }
+    dom = "gemm_wi_geglu"  # largest share of the algorithmic FLOPs (6HI of 8H^2+6HI per token per layer)
+    dom_ms = prof[dom]["ms"] / max(1, prof[dom]["launches"])
+    achieved_tf = gemm_flops[dom] / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    flops_pair = algorithmic_flops_per_pair(cfg, args.seq_len) if args.mode == "dense" else None
+    step_tf = (flops_pair * args.batch / (ms_per_step * 1e-3) / 1e12) if flops_pair else None
+    roofline = {
+        "bound": "tensor",
+        "kernel": "gemm_bf16_tcgen05_kernel<256, GEGLU> (mlp.Wi + GeGLU)",
+        "achieved": round(achieved_tf, 2),
+        "peak": peak_tf,
+        "unit": "TFLOP/s",
+        "frac": round(achieved_tf / peak_tf, 4),
+        "traffic": None,
+        "peak_kind": f"bf16 sustained, {peaks['source']} (MEASURED_PEAKS.json)",
+        "flops_per_launch": gemm_flops[dom],
+        "ms_per_launch": round(dom_ms, 4),
+        "all_gemms_tflops": {k: round(v / (prof[k]["ms"] / max(1, prof[k]["launches"]) * 1e-3) / 1e12, 1) for k, v in gemm_flops.items() if prof[k]["ms"] > 0},
+        "step_algorithmic_tflops": round(step_tf, 2) if step_tf else None,
+        "step_frac_of_burst_peak": round(step_tf / float(peaks["bf16_tflops"]), 4) if step_tf else None,
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import hf_cpu_baseline as hb
+
+        sd_cpu = syn.random_state_dict(cfg, seed=0)
+        model, head = hb.build_hf_model(cfg, sd_cpu)
+        res = hb.time_cpu_baseline(model, head, wl, args.cpu_pairs, THRESHOLD, warmup_pairs=1)
+        cpu_baseline = {
+            "value": round(res["pairs_per_s"], 4),
+            "unit": UNIT,
+            "cores": res["threads"],
+            "kind": "port",
+            "sample": f"first {args.cpu_pairs} blocks of the same workload ({res['seconds']:.1f} s), HF ModernBERT fp32 sdpa on CPU + numpy prune",
+            "host_cpus": os.cpu_count(),
+        }
+
+    line = {
+        "metric": METRIC,
+        "value": round(value, 2),
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(3, args.warmup),
+        "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": args.dtype,
+        "data": "synthetic",
+        "config": {
+            "workload": f"{args.model} seq_len={args.seq_len} batch={args.batch} blocks per GPU, {args.mode}, pre-tokenised, random-init weights",
+            "tokens_per_step_per_gpu": T,
+            "sentences_per_step_per_gpu": n_frags,
+            "threshold": THRESHOLD,
+            "parallelism": f"dp{world} (blocks sharded, weights replicated, one all-gather of scores per step)" if world > 1 else "single GPU",
+            "l2": "per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush",
+        },
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches) * args.steps,
+        "gpu_launches_per_step": int(launches),
+        "roofline": roofline,
+        "profile_ms_per_step": profile_ms,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -118,6 +118,26 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
                        int64_t n_tokens, int32_t max_seqlen, float* d_prune_logits, float* d_rank_logits,
                        void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Per-kernel-class timing of the forward, measured with CUDA events on the launch stream.
+ * Enable, run forwards, then collect (synchronises on the recorded events). */
+typedef enum opv_prof_class {
+  OPV_PROF_MISC = 0,        /* positions, unfused rope / geglu */
+  OPV_PROF_EMBED = 1,       /* embedding gather + LayerNorm */
+  OPV_PROF_LAYERNORM = 2,   /* attn_norm / mlp_norm */
+  OPV_PROF_GEMM_QKV = 3,    /* Wqkv (+RoPE) */
+  OPV_PROF_ATTN_GLOBAL = 4,
+  OPV_PROF_ATTN_LOCAL = 5,
+  OPV_PROF_GEMM_WO = 6,     /* attention Wo (+residual) */
+  OPV_PROF_GEMM_WI = 7,     /* mlp Wi (+GeGLU) */
+  OPV_PROF_GEMM_WO2 = 8,    /* mlp Wo (+residual) */
+  OPV_PROF_HEADS = 9,       /* final LN + prune head, rank head */
+  OPV_PROF_NUM_CLASSES = 10
+} opv_prof_class;
+int opv_profile_enable(opv_handle h, int32_t on);
+int opv_profile_collect(opv_handle h, float* h_ms, int32_t* h_launches, int32_t n_classes);
+/* Kernels launched by this engine since creation (forward only). */
+int64_t opv_launch_count(opv_handle h);
+
 /* Score conversion + per-fragment mean (standalone:2913-2920, 3075-3082).
  *   keep-prob p[t] = softmax(prune_logits[t])[1]; frag_mean[f] = mean(p[start_f:end_f]) or 1.0 when the
  *   range is empty; rank_score[s] = sigmoid(rank_logits[s, 0]).

@@ -16,6 +16,11 @@ OPV_DTYPE_BF16 = 0
 OPV_DTYPE_F32 = 1
 EPI_STORE, EPI_ROPE, EPI_RESIDUAL, EPI_GEGLU = 0, 1, 2, 3
 
+PROF_CLASSES = (
+    "misc", "embed_ln", "layernorm", "gemm_qkv_rope", "attention_global", "attention_local", "gemm_wo_residual",
+    "gemm_wi_geglu", "gemm_wo2_residual", "heads",
+)
+
 OPV_ERR_INVALID_ARGUMENT = -1
 OPV_ERR_UNSUPPORTED = -2
 OPV_ERR_CUDA = -3
@@ -82,6 +87,9 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_size_t, C.c_void_p],
     ),
+    "opv_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
+    "opv_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32]),
+    "opv_launch_count": (C.c_int64, [C.c_void_p]),
     "opv_fragment_means": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,

@@ -243,13 +243,43 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // ------------------------------------------------------------------------------------------------
 // engine
 // ------------------------------------------------------------------------------------------------
+struct ProfEvent {
+  int cls, n;
+  cudaEvent_t a, b;
+};
+
 struct opv_engine {
+  bool profiling = false;
+  int64_t launches = 0;
+  std::vector<ProfEvent> prof;
   opv_config cfg;
   opv_weights w;
   std::vector<opv_layer_weights> layers;
   std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_wi, tm_wo2;  // bf16 mode only
   int device;
   size_t elt;  // bytes per operand element
+};
+
+// Counts kernel launches and, when profiling is on, brackets them with CUDA events on the launch stream.
+struct LaunchScope {
+  opv_engine* e;
+  cudaStream_t s;
+  int cls, n;
+  cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(opv_engine* e_, cudaStream_t s_, int cls_, int n_ = 1) : e(e_), s(s_), cls(cls_), n(n_) {
+    e->launches += n;
+    if (e->profiling) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, s);
+    }
+  }
+  ~LaunchScope() {
+    if (a) {
+      cudaEventRecord(b, s);
+      e->prof.push_back({cls, n, a, b});
+    }
+  }
 };
 
 struct WorkspaceLayout {
@@ -388,56 +418,90 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
   void* u = ws + wl.u;
   int32_t* pos = reinterpret_cast<int32_t*>(ws + wl.pos);
   const int half_window = c.local_window / 2;
+  int rc = OPV_OK;
 
-  opv::positions_kernel<<<n_seqs, 256, 0, stream>>>(d_cu_seqlens, pos);
-  OPV_LAUNCH_CHECK("positions_kernel");
+  {
+    LaunchScope sc(e, stream, OPV_PROF_MISC);
+    opv::positions_kernel<<<n_seqs, 256, 0, stream>>>(d_cu_seqlens, pos);
+    OPV_LAUNCH_CHECK("positions_kernel");
+  }
 
   if (c.dtype == OPV_DTYPE_BF16) {
     using bf16 = __nv_bfloat16;
     const bool fused = c.fuse_epilogues != 0;
     CUtensorMap tm_x, tm_attn, tm_act;
-    if (int rc = make_tmap_bf16(&tm_x, x, T, H, opv::kGemmBlockM)) return rc;
-    if (int rc = make_tmap_bf16(&tm_attn, attn, T, H, opv::kGemmBlockM)) return rc;
-    if (int rc = make_tmap_bf16(&tm_act, act, T, I, opv::kGemmBlockM)) return rc;
-    if (int rc = launch_embed_ln<bf16, bf16>(d_ids, static_cast<const bf16*>(e->w.d_tok_embeddings), e->w.d_emb_norm,
-                                             h, static_cast<bf16*>(x), T, H, c.vocab_size, c.norm_eps, stream))
-      return rc;
+    if ((rc = make_tmap_bf16(&tm_x, x, T, H, opv::kGemmBlockM))) return rc;
+    if ((rc = make_tmap_bf16(&tm_attn, attn, T, H, opv::kGemmBlockM))) return rc;
+    if ((rc = make_tmap_bf16(&tm_act, act, T, I, opv::kGemmBlockM))) return rc;
+    {
+      LaunchScope sc(e, stream, OPV_PROF_EMBED);
+      rc = launch_embed_ln<bf16, bf16>(d_ids, static_cast<const bf16*>(e->w.d_tok_embeddings), e->w.d_emb_norm, h,
+                                       static_cast<bf16*>(x), T, H, c.vocab_size, c.norm_eps, stream);
+    }
+    if (rc) return rc;
     for (int l = 0; l < L; ++l) {
       const opv_layer_weights& lw = e->layers[l];
       const bool global = c.layer_is_global[l] != 0;
-      if (l > 0)
-        if (int rc = launch_layernorm<bf16>(h, lw.d_attn_norm, static_cast<bf16*>(x), T, H, c.norm_eps, stream))
-          return rc;
+      if (l > 0) {
+        LaunchScope sc(e, stream, OPV_PROF_LAYERNORM);
+        rc = launch_layernorm<bf16>(h, lw.d_attn_norm, static_cast<bf16*>(x), T, H, c.norm_eps, stream);
+      }
+      if (rc) return rc;
       opv::GemmEpilogueArgs ep{};
       ep.c = qkv, ep.ldc = 3 * H, ep.pos = pos, ep.rope_cols = 2 * H;
       ep.cos = global ? e->w.d_rope_cos_global : e->w.d_rope_cos_local;
       ep.sin = global ? e->w.d_rope_sin_global : e->w.d_rope_sin_local;
-      if (fused) {
-        if (int rc = gemm_bf16(opv::kEpiRope, tm_x, e->tm_wqkv[l], ep, T, 3 * H, H, stream)) return rc;
-      } else {
-        if (int rc = gemm_bf16(opv::kEpiStore, tm_x, e->tm_wqkv[l], ep, T, 3 * H, H, stream)) return rc;
+      {
+        LaunchScope sc(e, stream, OPV_PROF_GEMM_QKV);
+        rc = gemm_bf16(fused ? opv::kEpiRope : opv::kEpiStore, tm_x, e->tm_wqkv[l], ep, T, 3 * H, H, stream);
+      }
+      if (rc) return rc;
+      if (!fused) {
+        LaunchScope sc(e, stream, OPV_PROF_MISC);
         opv::rope_inplace_kernel<bf16><<<g_num_sms * 8, 256, 0, stream>>>(static_cast<bf16*>(qkv), pos, ep.cos, ep.sin, T, H);
         OPV_LAUNCH_CHECK("rope_inplace_kernel");
       }
-      if (int rc = launch_attention(OPV_DTYPE_BF16, qkv, attn, d_cu_seqlens, n_seqs, max_seqlen, heads,
-                                    global ? -1 : half_window, stream))
-        return rc;
+      {
+        LaunchScope sc(e, stream, global ? OPV_PROF_ATTN_GLOBAL : OPV_PROF_ATTN_LOCAL);
+        rc = launch_attention(OPV_DTYPE_BF16, qkv, attn, d_cu_seqlens, n_seqs, max_seqlen, heads,
+                              global ? -1 : half_window, stream);
+      }
+      if (rc) return rc;
       opv::GemmEpilogueArgs er{};
       er.c = h, er.ldc = H;
-      if (int rc = gemm_bf16(opv::kEpiResidual, tm_attn, e->tm_wo[l], er, T, H, H, stream)) return rc;
-      if (int rc = launch_layernorm<bf16>(h, lw.d_mlp_norm, static_cast<bf16*>(x), T, H, c.norm_eps, stream)) return rc;
+      {
+        LaunchScope sc(e, stream, OPV_PROF_GEMM_WO);
+        rc = gemm_bf16(opv::kEpiResidual, tm_attn, e->tm_wo[l], er, T, H, H, stream);
+      }
+      if (rc) return rc;
+      {
+        LaunchScope sc(e, stream, OPV_PROF_LAYERNORM);
+        rc = launch_layernorm<bf16>(h, lw.d_mlp_norm, static_cast<bf16*>(x), T, H, c.norm_eps, stream);
+      }
+      if (rc) return rc;
       if (fused) {
         opv::GemmEpilogueArgs eg{};
         eg.c = act, eg.ldc = I;
-        if (int rc = gemm_bf16(opv::kEpiGeglu, tm_x, e->tm_wi[l], eg, T, 2 * I, H, stream)) return rc;
+        LaunchScope sc(e, stream, OPV_PROF_GEMM_WI);
+        rc = gemm_bf16(opv::kEpiGeglu, tm_x, e->tm_wi[l], eg, T, 2 * I, H, stream);
       } else {
         opv::GemmEpilogueArgs es{};
         es.c = u, es.ldc = 2 * I;
-        if (int rc = gemm_bf16(opv::kEpiStore, tm_x, e->tm_wi[l], es, T, 2 * I, H, stream)) return rc;
+        {
+          LaunchScope sc(e, stream, OPV_PROF_GEMM_WI);
+          rc = gemm_bf16(opv::kEpiStore, tm_x, e->tm_wi[l], es, T, 2 * I, H, stream);
+        }
+        if (rc) return rc;
+        LaunchScope sc(e, stream, OPV_PROF_MISC);
         opv::geglu_kernel<bf16><<<g_num_sms * 8, 256, 0, stream>>>(static_cast<const bf16*>(u), static_cast<bf16*>(act), T, I);
         OPV_LAUNCH_CHECK("geglu_kernel");
       }
-      if (int rc = gemm_bf16(opv::kEpiResidual, tm_act, e->tm_wo2[l], er, T, H, I, stream)) return rc;
+      if (rc) return rc;
+      {
+        LaunchScope sc(e, stream, OPV_PROF_GEMM_WO2);
+        rc = gemm_bf16(opv::kEpiResidual, tm_act, e->tm_wo2[l], er, T, H, I, stream);
+      }
+      if (rc) return rc;
     }
   } else {
     float* xf = static_cast<float*>(x);
@@ -445,40 +509,101 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
     float* af = static_cast<float*>(attn);
     float* actf = static_cast<float*>(act);
     float* uf = static_cast<float*>(u);
-    if (int rc = launch_embed_ln<float, float>(d_ids, static_cast<const float*>(e->w.d_tok_embeddings),
-                                               e->w.d_emb_norm, h, xf, T, H, c.vocab_size, c.norm_eps, stream))
-      return rc;
+    {
+      LaunchScope sc(e, stream, OPV_PROF_EMBED);
+      rc = launch_embed_ln<float, float>(d_ids, static_cast<const float*>(e->w.d_tok_embeddings), e->w.d_emb_norm, h,
+                                         xf, T, H, c.vocab_size, c.norm_eps, stream);
+    }
+    if (rc) return rc;
     for (int l = 0; l < L; ++l) {
       const opv_layer_weights& lw = e->layers[l];
       const bool global = c.layer_is_global[l] != 0;
-      if (l > 0)
-        if (int rc = launch_layernorm<float>(h, lw.d_attn_norm, xf, T, H, c.norm_eps, stream)) return rc;
-      if (int rc = gemm_f32(false, xf, static_cast<const float*>(lw.d_wqkv), qf, T, 3 * H, H, 3 * H, stream)) return rc;
-      opv::rope_inplace_kernel<float><<<g_num_sms * 8, 256, 0, stream>>>(
-          qf, pos, global ? e->w.d_rope_cos_global : e->w.d_rope_cos_local,
-          global ? e->w.d_rope_sin_global : e->w.d_rope_sin_local, T, H);
-      OPV_LAUNCH_CHECK("rope_inplace_kernel");
-      if (int rc = launch_attention(OPV_DTYPE_F32, qf, af, d_cu_seqlens, n_seqs, max_seqlen, heads,
-                                    global ? -1 : half_window, stream))
-        return rc;
-      if (int rc = gemm_f32(true, af, static_cast<const float*>(lw.d_wo), h, T, H, H, H, stream)) return rc;
-      if (int rc = launch_layernorm<float>(h, lw.d_mlp_norm, xf, T, H, c.norm_eps, stream)) return rc;
-      if (int rc = gemm_f32(false, xf, static_cast<const float*>(lw.d_wi), uf, T, 2 * I, H, 2 * I, stream)) return rc;
-      opv::geglu_kernel<float><<<g_num_sms * 8, 256, 0, stream>>>(uf, actf, T, I);
-      OPV_LAUNCH_CHECK("geglu_kernel");
-      if (int rc = gemm_f32(true, actf, static_cast<const float*>(lw.d_wo2), h, T, H, I, H, stream)) return rc;
+      if (l > 0) {
+        LaunchScope sc(e, stream, OPV_PROF_LAYERNORM);
+        rc = launch_layernorm<float>(h, lw.d_attn_norm, xf, T, H, c.norm_eps, stream);
+      }
+      if (rc) return rc;
+      {
+        LaunchScope sc(e, stream, OPV_PROF_GEMM_QKV);
+        rc = gemm_f32(false, xf, static_cast<const float*>(lw.d_wqkv), qf, T, 3 * H, H, 3 * H, stream);
+      }
+      if (rc) return rc;
+      {
+        LaunchScope sc(e, stream, OPV_PROF_MISC);
+        opv::rope_inplace_kernel<float><<<g_num_sms * 8, 256, 0, stream>>>(
+            qf, pos, global ? e->w.d_rope_cos_global : e->w.d_rope_cos_local,
+            global ? e->w.d_rope_sin_global : e->w.d_rope_sin_local, T, H);
+        OPV_LAUNCH_CHECK("rope_inplace_kernel");
+      }
+      {
+        LaunchScope sc(e, stream, global ? OPV_PROF_ATTN_GLOBAL : OPV_PROF_ATTN_LOCAL);
+        rc = launch_attention(OPV_DTYPE_F32, qf, af, d_cu_seqlens, n_seqs, max_seqlen, heads,
+                              global ? -1 : half_window, stream);
+      }
+      if (rc) return rc;
+      {
+        LaunchScope sc(e, stream, OPV_PROF_GEMM_WO);
+        rc = gemm_f32(true, af, static_cast<const float*>(lw.d_wo), h, T, H, H, H, stream);
+      }
+      if (rc) return rc;
+      {
+        LaunchScope sc(e, stream, OPV_PROF_LAYERNORM);
+        rc = launch_layernorm<float>(h, lw.d_mlp_norm, xf, T, H, c.norm_eps, stream);
+      }
+      if (rc) return rc;
+      {
+        LaunchScope sc(e, stream, OPV_PROF_GEMM_WI);
+        rc = gemm_f32(false, xf, static_cast<const float*>(lw.d_wi), uf, T, 2 * I, H, 2 * I, stream);
+      }
+      if (rc) return rc;
+      {
+        LaunchScope sc(e, stream, OPV_PROF_MISC);
+        opv::geglu_kernel<float><<<g_num_sms * 8, 256, 0, stream>>>(uf, actf, T, I);
+        OPV_LAUNCH_CHECK("geglu_kernel");
+      }
+      {
+        LaunchScope sc(e, stream, OPV_PROF_GEMM_WO2);
+        rc = gemm_f32(true, actf, static_cast<const float*>(lw.d_wo2), h, T, H, I, H, stream);
+      }
+      if (rc) return rc;
     }
   }
 
-  if (int rc = launch_final_prune(h, e->w.d_final_norm, e->w.d_prune_weight, e->w.d_prune_bias, d_prune_logits, T, H,
-                                  c.norm_eps, stream))
-    return rc;
-  opv::rank_head_kernel<<<n_seqs, 256, (2 * H + 8) * sizeof(float), stream>>>(
-      h, d_cu_seqlens, e->w.d_final_norm, e->w.d_head_dense, e->w.d_head_norm, e->w.d_cls_weight, e->w.d_cls_bias,
-      d_rank_logits, H, c.num_labels, c.norm_eps);
-  OPV_LAUNCH_CHECK("rank_head_kernel");
+  {
+    LaunchScope sc(e, stream, OPV_PROF_HEADS, 2);
+    rc = launch_final_prune(h, e->w.d_final_norm, e->w.d_prune_weight, e->w.d_prune_bias, d_prune_logits, T, H,
+                            c.norm_eps, stream);
+    if (rc) return rc;
+    opv::rank_head_kernel<<<n_seqs, 256, (2 * H + 8) * sizeof(float), stream>>>(
+        h, d_cu_seqlens, e->w.d_final_norm, e->w.d_head_dense, e->w.d_head_norm, e->w.d_cls_weight, e->w.d_cls_bias,
+        d_rank_logits, H, c.num_labels, c.norm_eps);
+    OPV_LAUNCH_CHECK("rank_head_kernel");
+  }
   return OPV_OK;
 }
+
+int opv_profile_enable(opv_handle e, int32_t on) {
+  if (!e) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_profile_enable: null engine");
+  e->profiling = on != 0;
+  return OPV_OK;
+}
+
+int opv_profile_collect(opv_handle e, float* h_ms, int32_t* h_launches, int32_t n_classes) {
+  if (!e || !h_ms || !h_launches) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_profile_collect: null argument");
+  for (int i = 0; i < n_classes; ++i) h_ms[i] = 0.f, h_launches[i] = 0;
+  for (auto& ev : e->prof) {
+    OPV_CUDA(cudaEventSynchronize(ev.b));
+    float ms = 0.f;
+    OPV_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    if (ev.cls >= 0 && ev.cls < n_classes) h_ms[ev.cls] += ms, h_launches[ev.cls] += ev.n;
+    cudaEventDestroy(ev.a);
+    cudaEventDestroy(ev.b);
+  }
+  e->prof.clear();
+  return OPV_OK;
+}
+
+int64_t opv_launch_count(opv_handle e) { return e ? e->launches : 0; }
 
 int opv_fragment_means(const float* d_prune_logits, int64_t n_tokens, const int32_t* d_frag_ranges, int32_t n_frags,
                        float* d_frag_mean, const float* d_rank_logits, int32_t n_seqs, int32_t num_labels,

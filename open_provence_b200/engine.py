@@ -214,6 +214,22 @@ class Engine:
         except Exception:
             pass
 
+    # ------------------------------------------------------------------ profiling
+    def profile(self, on: bool) -> None:
+        """Bracket every forward launch with CUDA events on the launch stream (see ``profile_collect``)."""
+        N.check(self.lib.opv_profile_enable(self._handle, 1 if on else 0), "opv_profile_enable")
+
+    def profile_collect(self) -> dict[str, dict[str, float]]:
+        """{class: {"ms": total device ms, "launches": n}} since the last collect (synchronises)."""
+        n = len(N.PROF_CLASSES)
+        ms = (C.c_float * n)()
+        launches = (C.c_int32 * n)()
+        N.check(self.lib.opv_profile_collect(self._handle, ms, launches, n), "opv_profile_collect")
+        return {name: {"ms": float(ms[i]), "launches": int(launches[i])} for i, name in enumerate(N.PROF_CLASSES)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.opv_launch_count(self._handle))
+
     # ------------------------------------------------------------------ launches
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -286,3 +302,39 @@ class Engine:
                 )
             N.check(rc, "opv_sentence_prune")
         return prob, keep, near
+
+    # ------------------------------------------------------------------ host-buffer entry point
+    def score_packed_host(
+        self,
+        ids: torch.Tensor,
+        cu_seqlens: torch.Tensor,
+        max_seqlen: int,
+        frag_ranges: torch.Tensor,
+        sent_offsets: torch.Tensor,
+        sent_frag_index: torch.Tensor,
+        threshold: float,
+        guard: float = 1e-5,
+    ) -> dict[str, torch.Tensor]:
+        """The whole hot path on HOST buffers (CPU int32 tensors, ideally pinned): H2D copies, forward,
+        score conversion, per-sentence prune, D2H of the results.  Synchronises before returning.
+
+        Returns CPU tensors: ``rank_score`` fp32 [n_blocks], ``sent_prob`` fp64 [n_sents],
+        ``keep`` uint8 [n_sents], ``near`` uint8 [n_sents] (|prob - threshold| <= guard).
+        """
+        dev = self.device
+        d_ids = ids.to(dev, non_blocking=True)
+        d_cu = cu_seqlens.to(dev, non_blocking=True)
+        d_ranges = frag_ranges.to(dev, non_blocking=True)
+        d_off = sent_offsets.to(dev, non_blocking=True)
+        d_idx = sent_frag_index.to(dev, non_blocking=True)
+        prune, rank = self.forward_packed(d_ids, d_cu, max_seqlen)
+        frag_mean, score = self.fragment_means(prune, d_ranges, rank)
+        prob, keep, near = self.sentence_prune(frag_mean, d_off, d_idx, threshold, guard)
+        out = {
+            "rank_score": score.to("cpu", non_blocking=True),
+            "sent_prob": prob.to("cpu", non_blocking=True),
+            "keep": keep.to("cpu", non_blocking=True),
+            "near": near.to("cpu", non_blocking=True),
+        }
+        torch.cuda.current_stream(dev).synchronize()
+        return out
