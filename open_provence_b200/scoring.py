@@ -1,0 +1,166 @@
+"""Block scoring: the device side of ``process()``.
+
+``process()`` hands a :class:`BlockTable` (token ids per block, fragment ranges, sentence -> fragment
+CSR) to a *scorer* and gets back per-block rerank scores and per-sentence keep decisions.  The only
+scorer shipped is :class:`DeviceScorer` (the sm_100a engine); tests inject recorded-logit scorers at the
+same seam the reference's tests use (they monkeypatch ``OpenProvenceModel.forward``).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any
+
+import numpy as np
+import torch
+
+
+@dataclass
+class BlockTable:
+    """Everything the hot path needs about a ``process()`` call, in flat arrays."""
+
+    block_ids: list[np.ndarray] = field(default_factory=list)  # int32 token ids per block
+    frag_block: list[int] = field(default_factory=list)  # block index of every fragment slot
+    frag_local: list[tuple[int, int]] = field(default_factory=list)  # block-local [start, end)
+    sent_offsets: list[int] = field(default_factory=lambda: [0])  # CSR over sentences
+    sent_frag_index: list[int] = field(default_factory=list)  # fragment slots of each sentence
+
+    @property
+    def n_blocks(self) -> int:
+        return len(self.block_ids)
+
+    @property
+    def n_sentences(self) -> int:
+        return len(self.sent_offsets) - 1
+
+
+def plan_launches(lengths: list[int], max_tokens: int, max_blocks: int = 65535) -> list[tuple[int, int]]:
+    """Consecutive [begin, end) block ranges with at most ``max_tokens`` packed tokens each."""
+    out: list[tuple[int, int]] = []
+    begin, tokens = 0, 0
+    for i, n in enumerate(lengths):
+        if i > begin and (tokens + n > max_tokens or i - begin >= max_blocks):
+            out.append((begin, i))
+            begin, tokens = i, 0
+        tokens += n
+    if begin < len(lengths):
+        out.append((begin, len(lengths)))
+    return out
+
+
+def exact_fragment_mean(logits: np.ndarray) -> float:
+    """The reference's arithmetic for one fragment, bit for bit (standalone:2918-2920, 3081):
+    torch CPU fp32 softmax over the two logits, column 1, numpy fp32 mean."""
+    if logits.shape[0] == 0:
+        return 1.0
+    probs = torch.softmax(torch.from_numpy(np.ascontiguousarray(logits, dtype=np.float32)), dim=-1).numpy()[:, 1]
+    return float(probs.mean())
+
+
+def exact_sentence_probability(frag_means: list[float]) -> float:
+    """standalone:3118-3119."""
+    avg = float(np.mean(frag_means)) if frag_means else 0.0
+    return max(0.0, min(avg, 1.0))
+
+
+class DeviceScorer:
+    """Runs a :class:`BlockTable` on an :class:`~open_provence_b200.engine.Engine`.
+
+    Blocks are packed unpadded into launches of at most ``max_tokens`` tokens (host -> device once per
+    launch), fragment means are reduced on the device, the per-sentence prune runs on the device for all
+    sentences of the call, and only ``(rank_score, sentence_prob, keep)`` cross PCIe.  Sentences whose
+    probability lands within ``guard`` of the threshold are re-evaluated on the host from their fp32
+    logits with the reference's exact procedure, so keep decisions are a pure function of the logits.
+    """
+
+    def __init__(self, engine: Any, max_tokens: int = 131072, guard: float = 1e-5) -> None:
+        self.engine = engine
+        self.max_tokens = int(max_tokens)
+        self.guard = float(guard)
+
+    def run(self, table: BlockTable, threshold: float) -> dict[str, np.ndarray]:
+        """Single-GPU path: score every block, then prune."""
+        rank_score, frag_mean_dev, kept = self.score_blocks(table, np.arange(table.n_blocks))
+        return self.prune(table, rank_score, frag_mean_dev, kept, threshold)
+
+    def score_blocks(self, table: BlockTable, blocks: np.ndarray):
+        """Forward + score conversion + fragment means for ``blocks`` (indices into the table).
+
+        Returns ``(rank_score np.float32 [n_blocks], frag_mean cuda fp32 [F], kept_logits)``; entries of
+        blocks that were not requested stay 0 (filled in by the all-gather in the sharded path)."""
+        eng = self.engine
+        dev = eng.device
+        n_blocks = table.n_blocks
+        lengths = [int(b.shape[0]) for b in table.block_ids]
+        frag_block = np.asarray(table.frag_block, dtype=np.int64)
+        frag_local = np.asarray(table.frag_local, dtype=np.int64).reshape(-1, 2)
+        n_frags = frag_block.shape[0]
+        rank_score = np.zeros(n_blocks, dtype=np.float32)
+        frag_mean_dev = torch.zeros(max(n_frags, 1), dtype=torch.float32, device=dev)
+        order = np.argsort(frag_block, kind="stable")  # fragment slots grouped by block
+        first_slot = np.searchsorted(frag_block[order], np.arange(n_blocks + 1))
+        kept_logits: list[tuple] = []
+
+        blocks = np.asarray(blocks, dtype=np.int64)
+        sub_lengths = [lengths[b] for b in blocks]
+        pending: list[tuple[np.ndarray, torch.Tensor]] = []
+        for lo, hi in plan_launches(sub_lengths, self.max_tokens):
+            chunk = blocks[lo:hi]
+            cu = np.zeros(len(chunk) + 1, dtype=np.int32)
+            np.cumsum([lengths[b] for b in chunk], out=cu[1:])
+            ids = np.concatenate([table.block_ids[b] for b in chunk]).astype(np.int32, copy=False)
+            counts = [int(first_slot[b + 1] - first_slot[b]) for b in chunk]
+            slots = np.concatenate([order[first_slot[b] : first_slot[b + 1]] for b in chunk]) if n_frags else np.zeros(0, np.int64)
+            base = np.repeat(cu[:-1].astype(np.int64), counts)
+            ranges = (frag_local[slots] + base[:, None]).astype(np.int32) if slots.size else np.zeros((0, 2), np.int32)
+            d_ids = torch.from_numpy(ids).to(dev, non_blocking=True)
+            d_cu = torch.from_numpy(cu).to(dev, non_blocking=True)
+            d_ranges = torch.from_numpy(np.ascontiguousarray(ranges)).to(dev, non_blocking=True)
+            prune, rank = eng.forward_packed(d_ids, d_cu, int(max(lengths[b] for b in chunk)))
+            means, score = eng.fragment_means(prune, d_ranges, rank)
+            if slots.size:
+                frag_mean_dev[torch.from_numpy(slots).to(dev)] = means
+            pending.append((chunk, score))
+            kept_logits.append((ranges, slots, prune))
+        for chunk, score in pending:  # one sync at the end instead of one per launch
+            rank_score[chunk] = score.cpu().numpy()
+        return rank_score, frag_mean_dev, kept_logits
+
+    def prune(self, table: BlockTable, rank_score: np.ndarray, frag_mean_dev: torch.Tensor, kept_logits: list,
+              threshold: float) -> dict[str, np.ndarray]:
+        """Per-sentence mean / threshold on the device for every sentence of the call."""
+        eng = self.engine
+        dev = eng.device
+        n_frags = len(table.frag_block)
+        sent_offsets = np.asarray(table.sent_offsets, dtype=np.int32)
+        sent_index = np.asarray(table.sent_frag_index, dtype=np.int32)
+        n_sent = table.n_sentences
+        if n_sent > 0:
+            d_off = torch.from_numpy(sent_offsets).to(dev)
+            d_idx = torch.from_numpy(sent_index if sent_index.size else np.zeros(1, np.int32)).to(dev)
+            prob, keep, near = eng.sentence_prune(frag_mean_dev, d_off, d_idx, threshold, self.guard)
+            prob_h = prob.cpu().numpy()
+            keep_h = keep.cpu().numpy().astype(bool)
+            near_h = near.cpu().numpy().astype(bool)
+        else:
+            prob_h, keep_h, near_h = np.zeros(0), np.zeros(0, bool), np.zeros(0, bool)
+        frag_mean_h = frag_mean_dev[:n_frags].cpu().numpy() if n_frags else np.zeros(0, np.float32)
+
+        if near_h.any():  # rare: re-evaluate with the reference's exact CPU arithmetic
+            needed = set()
+            for s in np.nonzero(near_h)[0]:
+                needed.update(int(k) for k in sent_index[sent_offsets[s] : sent_offsets[s + 1]])
+            slot_mean: dict[int, float] = {}
+            for ranges, slots, prune in kept_logits:
+                for j, slot in enumerate(slots):
+                    if int(slot) in needed:
+                        a, b = int(ranges[j, 0]), int(ranges[j, 1])
+                        logits = prune[a:b].cpu().numpy() if b > a else np.zeros((0, 2), np.float32)
+                        slot_mean[int(slot)] = exact_fragment_mean(logits)
+            for s in np.nonzero(near_h)[0]:
+                members = [int(k) for k in sent_index[sent_offsets[s] : sent_offsets[s + 1]]]
+                # fragments scored on another rank have no local logits: keep their device mean
+                exact = exact_sentence_probability([slot_mean.get(k, float(frag_mean_h[k])) for k in members])
+                prob_h[s] = exact
+                keep_h[s] = exact > threshold
+        return {"rank_score": rank_score, "frag_mean": frag_mean_h, "sent_prob": prob_h, "keep": keep_h, "near": near_h}

@@ -1,0 +1,192 @@
+"""End to end on the GPU: ``from_pretrained`` -> ``process()`` / ``forward()`` against the reference's results."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from open_provence_b200.host_text import simple_sentence_splitter  # noqa: E402
+from open_provence_b200.modeling import OpenProvenceModel  # noqa: E402
+from open_provence_b200.scoring import BlockTable, DeviceScorer  # noqa: E402
+from oracle import postprocess_numpy as opp  # noqa: E402
+
+CASES = [
+    "str_str", "str_list", "aligned", "nested", "presplit_sentences", "explicit_titles", "first_line_title",
+    "title_none", "multi_block", "multi_block_respect", "overlong_sentence", "strip_sentences", "reorder_topk",
+    "no_best_score", "japanese", "empty_context", "batch_size_1",
+]
+
+
+@pytest.fixture(scope="module")
+def model_fp32(tiny_ckpt_dir):
+    return OpenProvenceModel.from_pretrained(tiny_ckpt_dir, device="cuda", dtype="fp32")
+
+
+@pytest.fixture(scope="module")
+def model_bf16(tiny_ckpt_dir):
+    return OpenProvenceModel.from_pretrained(tiny_ckpt_dir, device="cuda")
+
+
+def _flatten(x):
+    if isinstance(x, (list, tuple)):
+        out = []
+        for v in x:
+            out.extend(_flatten(v))
+        return out
+    return [x]
+
+
+def _run(model, case):
+    kwargs = dict(case["kwargs"])
+    kwargs["sentence_splitter"] = simple_sentence_splitter
+    model.max_length = case["max_length"]
+    return model.process(**kwargs)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_process_fp32_identical_to_reference(name, process_golden, model_fp32):
+    """fp32 engine: pruned text / kept sentence sets bit-exact, probabilities within 1e-5."""
+    case = next(c for c in process_golden["cases"] if c["name"] == name)
+    res = _run(model_fp32, case)
+    gold = case["result"]
+    assert res["pruned_context"] == gold["pruned_context"]
+    assert res["kept_sentences"] == gold["kept_sentences"]
+    assert res["removed_sentences"] == gold["removed_sentences"]
+    assert res["title"] == gold["title"]
+    a, b = _flatten(res["sentence_probabilities"]), _flatten(gold["sentence_probabilities"])
+    assert len(a) == len(b)
+    assert max((abs(x - y) for x, y in zip(a, b)), default=0.0) < 1e-5
+    sa, sb = _flatten(res["reranking_score"]), _flatten(gold["reranking_score"])
+    assert all((x is None) == (y is None) for x, y in zip(sa, sb))
+    assert max((abs(x - y) for x, y in zip(sa, sb) if x is not None), default=0.0) < 1e-5
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_process_bf16_close_to_reference(name, process_golden, model_bf16):
+    """bf16 engine: probabilities within 1e-2; keep decisions identical wherever the reference's probability is
+    further than that from the threshold."""
+    case = next(c for c in process_golden["cases"] if c["name"] == name)
+    res = _run(model_bf16, case)
+    gold = case["result"]
+    a, b = _flatten(res["sentence_probabilities"]), _flatten(gold["sentence_probabilities"])
+    assert len(a) == len(b)
+    err = max((abs(x - y) for x, y in zip(a, b)), default=0.0)
+    assert err < 1e-2, f"sentence probability error {err:.3e}"
+    thr = case["kwargs"]["threshold"]
+    if all(abs(y - thr) > 1e-2 for y in b):
+        assert res["kept_sentences"] == gold["kept_sentences"]
+        assert res["pruned_context"] == gold["pruned_context"]
+    sa, sb = _flatten(res["reranking_score"]), _flatten(gold["reranking_score"])
+    assert max((abs(x - y) for x, y in zip(sa, sb) if x is not None and y is not None), default=0.0) < 5e-3
+
+
+def test_forward_padded_interface(model_fp32, forward_golden):
+    """``forward(input_ids, attention_mask)`` keeps the reference's [B, S] interface (standalone:1666-1739)."""
+    ids = torch.from_numpy(forward_golden["input_ids"])
+    mask = torch.from_numpy(forward_golden["attention_mask"])
+    out = model_fp32.forward(input_ids=ids, attention_mask=mask, return_dict=True, token_type_ids=torch.zeros_like(ids))
+    assert out.ranking_logits.shape == (ids.shape[0], 1) and out.pruning_logits.shape == (*ids.shape, 2)
+    assert out["ranking_logits"] is out.logits
+    rank = out.ranking_logits.cpu().double().numpy()
+    prune = out.pruning_logits.cpu().double().numpy()
+    m = forward_golden["attention_mask"][..., None]
+    assert np.abs(rank - forward_golden["ranking_logits_f64"]).max() < 1e-5
+    assert np.abs((prune - forward_golden["pruning_logits_f64"]) * m).max() < 1e-5
+    tup = model_fp32.forward(input_ids=ids, attention_mask=mask, return_dict=False)
+    assert isinstance(tup, tuple) and len(tup) == 2
+    with pytest.raises(ValueError, match="input_ids must be provided"):
+        model_fp32.forward(input_ids=None)
+    bad = mask.clone()
+    bad[-1, 0] = 0
+    with pytest.raises(ValueError, match="right-padded"):
+        model_fp32.forward(input_ids=ids, attention_mask=bad)
+
+
+def test_prune_kernels_match_oracle(model_fp32):
+    """fragment means / sentence prune on the device vs the numpy restatement, incl. empty ranges,
+    sentences without fragments and the guard-band re-evaluation at an exact threshold tie."""
+    eng = model_fp32.engine
+    rng = np.random.default_rng(3)
+    n_tokens = 5000
+    logits = rng.normal(0, 3, size=(n_tokens, 2)).astype(np.float32)
+    rank_logits = rng.normal(0, 2, size=(7, 1)).astype(np.float32)
+    ranges, at = [], 0
+    while at < n_tokens - 60:
+        step = int(rng.integers(1, 60))
+        ranges.append((at, at + step))
+        at += step
+    ranges += [(10, 10), (20, 5), (n_tokens - 3, n_tokens + 50)]  # empty, inverted, clipped
+    ranges = np.asarray(ranges, dtype=np.int32)
+    d_logits = torch.from_numpy(logits).cuda()
+    frag_mean, score = eng.fragment_means(d_logits, torch.from_numpy(ranges).cuda(), torch.from_numpy(rank_logits).cuda())
+    probs = opp.keep_probs_from_logits(logits)
+    ref = []
+    for s, e in ranges:
+        s, e = max(0, min(int(s), n_tokens)), min(int(e), n_tokens)
+        e = max(s, e)
+        ref.append(1.0 if e <= s else float(probs[s:e].mean()))
+    torch.cuda.synchronize()
+    assert np.abs(frag_mean.cpu().numpy() - np.asarray(ref)).max() < 2e-6
+    ref_score = [opp.ranking_score_from_logits(r) for r in rank_logits]
+    assert np.abs(score.cpu().numpy() - np.asarray(ref_score)).max() < 1e-6
+
+    # sentences: groups of 1..4 fragments, plus one sentence with no fragment at all
+    offsets, index = [0], []
+    f = 0
+    while f < len(ranges):
+        k = int(rng.integers(1, 5))
+        index.extend(range(f, min(f + k, len(ranges))))
+        offsets.append(len(index))
+        f += k
+    offsets.append(len(index))  # empty sentence
+    fm = frag_mean.cpu().numpy()
+    ref_prob = [max(0.0, min(float(np.mean(fm[index[a:b]])) if b > a else 0.0, 1.0)) for a, b in zip(offsets[:-1], offsets[1:])]
+    thr = ref_prob[3]  # exact tie: reference says "not kept" (strict >)
+    prob, keep, near = eng.sentence_prune(frag_mean, torch.tensor(offsets, dtype=torch.int32).cuda(),
+                                          torch.tensor(index, dtype=torch.int32).cuda(), thr, 1e-5)
+    torch.cuda.synchronize()
+    assert np.abs(prob.cpu().numpy() - np.asarray(ref_prob)).max() < 1e-12
+    assert near.cpu().numpy()[3] == 1
+    far = np.abs(np.asarray(ref_prob) - thr) > 1e-5
+    assert np.array_equal(keep.cpu().numpy().astype(bool)[far], (np.asarray(ref_prob) > thr)[far])
+    assert prob.cpu().numpy()[-1] == 0.0 and keep.cpu().numpy()[-1] == 0
+
+
+def test_device_scorer_guard_band_matches_exact_reference_procedure(model_fp32):
+    """A sentence sitting exactly on the threshold is re-evaluated with torch-CPU softmax + numpy mean."""
+    eng = model_fp32.engine
+    rng = np.random.default_rng(5)
+    table = BlockTable()
+    for b in range(3):
+        n = 40 + 10 * b
+        ids = rng.integers(5, 260, size=n).astype(np.int32)
+        ids[0] = 1
+        table.block_ids.append(ids)
+        for s in range(4):
+            table.frag_block.append(b)
+            table.frag_local.append((2 + 8 * s, 2 + 8 * s + 8))
+            table.sent_frag_index.append(len(table.frag_block) - 1)
+            table.sent_offsets.append(len(table.sent_frag_index))
+    scorer = DeviceScorer(eng)
+    first = scorer.run(table, 0.5)
+    target = 5
+    thr = float(first["sent_prob"][target])
+    second = scorer.run(table, thr)
+    assert bool(second["near"][target])
+    # the re-evaluation uses the reference's exact CPU procedure on the engine's own fp32 logits
+    from open_provence_b200.scoring import exact_fragment_mean, exact_sentence_probability
+
+    blk = table.frag_block[target]
+    ids = torch.from_numpy(table.block_ids[blk]).cuda()
+    cu = torch.tensor([0, ids.numel()], dtype=torch.int32, device="cuda")
+    prune, _ = eng.forward_packed(ids, cu, int(ids.numel()))
+    a, b = table.frag_local[target]
+    exact = exact_sentence_probability([exact_fragment_mean(prune[a:b].cpu().numpy())])
+    assert second["sent_prob"][target] == exact
+    assert bool(second["keep"][target]) == (exact > thr)
+    assert abs(exact - thr) < 1e-6
+    others = np.abs(first["sent_prob"] - thr) > 1e-5
+    assert np.array_equal(second["keep"][others], (first["sent_prob"] > thr)[others])
