@@ -143,7 +143,7 @@ def test_prune_kernels_match_oracle(model_fp32):
         f += k
     offsets.append(len(index))  # empty sentence
     fm = frag_mean.cpu().numpy()
-    ref_prob = [max(0.0, min(float(np.mean(fm[index[a:b]])) if b > a else 0.0, 1.0)) for a, b in zip(offsets[:-1], offsets[1:])]
+    ref_prob = [max(0.0, min(float(np.mean([float(v) for v in fm[index[a:b]]])) if b > a else 0.0, 1.0)) for a, b in zip(offsets[:-1], offsets[1:])]
     thr = ref_prob[3]  # exact tie: reference says "not kept" (strict >)
     prob, keep, near = eng.sentence_prune(frag_mean, torch.tensor(offsets, dtype=torch.int32).cuda(),
                                           torch.tensor(index, dtype=torch.int32).cuda(), thr, 1e-5)
