@@ -118,6 +118,11 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
                        int64_t n_tokens, int32_t max_seqlen, float* d_prune_logits, float* d_rank_logits,
                        void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Process-wide tuning switches (tests, profiling).  "attention_impl": bf16 attention kernel,
+ * 0 = mma.sync flash kernel (v1), 1 = tcgen05 kernel with P in TMEM (default), 2 = tcgen05 kernel with P
+ * staged through shared memory. */
+int opv_set_option(const char* name, int64_t value);
+
 /* Per-kernel-class timing of the forward, measured with CUDA events on the launch stream.
  * Enable, run forwards, then collect (synchronises on the recorded events). */
 typedef enum opv_prof_class {
@@ -178,7 +183,7 @@ int opv_op_embed_ln(int32_t dtype, const int32_t* d_ids, const void* d_emb, cons
                     void* d_x, int64_t m, int32_t hidden, int32_t vocab, float eps, void* stream);
 /* Varlen attention over packed qkv [T, 3H] (RoPE already applied) -> out [T, H]. window < 0 = global. */
 int opv_op_attention(int32_t dtype, const void* d_qkv, void* d_out, const int32_t* d_cu_seqlens, int32_t n_seqs,
-                     int32_t max_seqlen, int32_t num_heads, int32_t half_window, void* stream);
+                     int64_t n_tokens, int32_t max_seqlen, int32_t num_heads, int32_t half_window, void* stream);
 /* In-place RoPE on the q,k thirds of qkv [T, 3H] (unfused path). */
 int opv_op_rope(int32_t dtype, void* d_qkv, const int32_t* d_pos, const float* d_cos, const float* d_sin,
                 int64_t m, int32_t hidden, void* stream);

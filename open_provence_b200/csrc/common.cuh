@@ -32,6 +32,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Register re-partitioning between warpgroups (all 4 warps of a warpgroup execute the same one).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2, flush-to-zero; -inf -> 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // exact-erf GELU, HF ACT2FN["gelu"] (HF:85); erff is accurate to ~1 ulp
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
@@ -146,12 +161,31 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Shared-memory matrix descriptor for an MN-major operand tile written by TMA with SWIZZLE_128B:
+// rows = K index (here: keys), each row 64 bf16 (128 B) of the MN dimension, 8-row groups of 1024 B.
+// Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16 B units (cute mma_traits_sm100.hpp
+// make_umma_desc<Major::MN>): SBO = 1024 B between 8-row groups along K; LBO only matters for MN > 64.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>(1024 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major, dense.
 // (cute::UMMA::InstrDescriptor) c_format[4,6)=1 (F32), a_format[7,10)=1 (BF16), b_format[10,13)=1,
 // a_major bit15 = 0, b_major bit16 = 0, n_dim[17,23) = N>>3, m_dim[24,29) = M>>4.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// Same, with the B operand MN-major (bit 16): used for P.V where V is stored [keys, head_dim].
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_bmn(int m, int n) {
+  return umma_idesc_bf16_f32(m, n) | (1u << 16);
 }
 
 // D[tmem] (+)= A[smem] . B[smem]^T, issued by ONE thread.
@@ -165,6 +199,20 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t a_desc, u
       "}\n"
       :
       : "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]: A is a K-major bf16 tile held in TMEM (lane = row, two K
+// elements per 32-bit column), issued by ONE thread.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // Arrive on `bar` when all previously issued tcgen05.mma of this thread have completed.

@@ -13,6 +13,7 @@
 
 #include "../../include/opv.h"
 #include "attention.cuh"
+#include "attention_tcgen05.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tcgen05.cuh"
@@ -88,6 +89,8 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 
 int g_num_sms = 0;
 bool g_attrs_set = false;
+// bf16 attention kernel: 0 = mma.sync v1, 1 = tcgen05 with P in TMEM (default), 2 = tcgen05 with P in smem
+int g_attention_impl = 1;
 
 template <int BLOCK_N, int EPI>
 int set_gemm_attr() {
@@ -113,6 +116,10 @@ int ensure_device_setup() {
   if (int rc = set_gemm_attr<128, opv::kEpiStore>()) return rc;
   if (int rc = set_gemm_attr<128, opv::kEpiRope>()) return rc;
   if (int rc = set_gemm_attr<128, opv::kEpiResidual>()) return rc;
+  OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                opv::FaSmemLayout<true>::kTotal));
+  OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                opv::FaSmemLayout<false>::kTotal));
   g_attrs_set = true;
   return OPV_OK;
 }
@@ -217,12 +224,23 @@ int launch_final_prune(const float* h, const float* w, const float* wp, const fl
   return OPV_OK;
 }
 
+// tm_qkv: TMA map of the packed qkv [T, 3H] buffer with a 128-row x 64-column box (tcgen05 kernels only)
 int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, int n_seqs, int max_seqlen, int heads,
-                     int half_window, cudaStream_t s) {
+                     int half_window, const CUtensorMap* tm_qkv, cudaStream_t s) {
   if (n_seqs <= 0 || max_seqlen <= 0) return OPV_OK;
   if (n_seqs > 65535) return fail(OPV_ERR_UNSUPPORTED, "at most 65535 sequences per launch");
   const int H = heads * 64;
-  if (dtype == OPV_DTYPE_BF16) {
+  if (dtype == OPV_DTYPE_BF16 && g_attention_impl != 0) {
+    if (!tm_qkv) return fail(OPV_ERR_INVALID_ARGUMENT, "tcgen05 attention needs the qkv tensor map");
+    dim3 grid((max_seqlen + opv::kFaBlockM - 1) / opv::kFaBlockM, heads, n_seqs);
+    if (g_attention_impl == 1)
+      opv::attention_tcgen05_kernel<true><<<grid, opv::kFaThreads, opv::FaSmemLayout<true>::kTotal, s>>>(
+          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window);
+    else
+      opv::attention_tcgen05_kernel<false><<<grid, opv::kFaThreads, opv::FaSmemLayout<false>::kTotal, s>>>(
+          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window);
+    OPV_LAUNCH_CHECK("attention_tcgen05_kernel");
+  } else if (dtype == OPV_DTYPE_BF16) {
     dim3 grid((max_seqlen + opv::kAttBlockM - 1) / opv::kAttBlockM, heads, n_seqs);
     opv::attention_mma_kernel<<<grid, opv::kAttThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv),
                                                                 static_cast<__nv_bfloat16*>(out), cu, H, half_window);
@@ -429,7 +447,8 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
   if (c.dtype == OPV_DTYPE_BF16) {
     using bf16 = __nv_bfloat16;
     const bool fused = c.fuse_epilogues != 0;
-    CUtensorMap tm_x, tm_attn, tm_act;
+    CUtensorMap tm_x, tm_attn, tm_act, tm_qkv;
+    if ((rc = make_tmap_bf16(&tm_qkv, qkv, T, 3 * H, opv::kFaBlockM))) return rc;
     if ((rc = make_tmap_bf16(&tm_x, x, T, H, opv::kGemmBlockM))) return rc;
     if ((rc = make_tmap_bf16(&tm_attn, attn, T, H, opv::kGemmBlockM))) return rc;
     if ((rc = make_tmap_bf16(&tm_act, act, T, I, opv::kGemmBlockM))) return rc;
@@ -464,7 +483,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       {
         LaunchScope sc(e, stream, global ? OPV_PROF_ATTN_GLOBAL : OPV_PROF_ATTN_LOCAL);
         rc = launch_attention(OPV_DTYPE_BF16, qkv, attn, d_cu_seqlens, n_seqs, max_seqlen, heads,
-                              global ? -1 : half_window, stream);
+                              global ? -1 : half_window, &tm_qkv, stream);
       }
       if (rc) return rc;
       opv::GemmEpilogueArgs er{};
@@ -538,7 +557,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       {
         LaunchScope sc(e, stream, global ? OPV_PROF_ATTN_GLOBAL : OPV_PROF_ATTN_LOCAL);
         rc = launch_attention(OPV_DTYPE_F32, qf, af, d_cu_seqlens, n_seqs, max_seqlen, heads,
-                              global ? -1 : half_window, stream);
+                              global ? -1 : half_window, nullptr, stream);
       }
       if (rc) return rc;
       {
@@ -686,9 +705,27 @@ int opv_op_embed_ln(int32_t dtype, const int32_t* d_ids, const void* d_emb, cons
 }
 
 int opv_op_attention(int32_t dtype, const void* d_qkv, void* d_out, const int32_t* d_cu_seqlens, int32_t n_seqs,
-                     int32_t max_seqlen, int32_t num_heads, int32_t half_window, void* stream_) {
+                     int64_t n_tokens, int32_t max_seqlen, int32_t num_heads, int32_t half_window, void* stream_) {
+  if (!d_qkv || !d_out || !d_cu_seqlens) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_op_attention: null buffer");
+  if (int rc = ensure_device_setup()) return rc;
+  CUtensorMap tm_qkv;
+  const bool tc = dtype == OPV_DTYPE_BF16 && g_attention_impl != 0;
+  if (tc) {
+    if (n_tokens <= 0) return OPV_OK;
+    if (int rc = make_tmap_bf16(&tm_qkv, d_qkv, n_tokens, 3 * num_heads * 64, opv::kFaBlockM)) return rc;
+  }
   return launch_attention(dtype, d_qkv, d_out, d_cu_seqlens, n_seqs, max_seqlen, num_heads, half_window,
-                          static_cast<cudaStream_t>(stream_));
+                          tc ? &tm_qkv : nullptr, static_cast<cudaStream_t>(stream_));
+}
+
+int opv_set_option(const char* name, int64_t value) {
+  if (!name) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_set_option: null name");
+  if (strcmp(name, "attention_impl") == 0) {
+    if (value < 0 || value > 2) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_impl must be 0, 1 or 2");
+    g_attention_impl = static_cast<int>(value);
+    return OPV_OK;
+  }
+  return fail(OPV_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
 }
 
 int opv_op_rope(int32_t dtype, void* d_qkv, const int32_t* d_pos, const float* d_cos, const float* d_sin, int64_t m,

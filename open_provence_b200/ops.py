@@ -86,7 +86,7 @@ def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, num_
     out = torch.empty((t, num_heads * 64), dtype=qkv.dtype, device=qkv.device)
     with torch.cuda.device(qkv.device):
         rc = lib.opv_op_attention(_code(qkv), qkv.data_ptr(), out.data_ptr(), cu_seqlens.data_ptr(),
-                                  cu_seqlens.numel() - 1, max_seqlen, num_heads, half_window, _stream(qkv))
+                                  cu_seqlens.numel() - 1, t, max_seqlen, num_heads, half_window, _stream(qkv))
     N.check(rc, "opv_op_attention")
     return out
 
@@ -117,3 +117,8 @@ def positions(cu_seqlens: torch.Tensor, n_tokens: int) -> torch.Tensor:
         rc = lib.opv_op_positions(cu_seqlens.data_ptr(), cu_seqlens.numel() - 1, pos.data_ptr(), _stream(cu_seqlens))
     N.check(rc, "opv_op_positions")
     return pos
+
+
+def set_option(name: str, value: int) -> None:
+    """Process-wide tuning switch of the library (see ``opv_set_option`` in include/opv.h)."""
+    N.check(N.load().opv_set_option(name.encode(), int(value)), "opv_set_option")

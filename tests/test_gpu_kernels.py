@@ -187,6 +187,31 @@ def test_attention(dtype, half_window):
     assert torch.isfinite(out.float()).all()
 
 
+@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("half_window", [-1, 64])
+def test_attention_bf16_impls(impl, half_window):
+    """All three bf16 kernels (mma.sync v1, tcgen05 with P in TMEM, tcgen05 with P in smem) on ragged lengths
+    that cross the 128-row tile and 128-key block boundaries, plus a multi-block sequence."""
+    heads = 3
+    lengths = ATT_LENGTHS + [1100]
+    total = sum(lengths)
+    g = torch.Generator().manual_seed(15)
+    qkv = (torch.randn((total, 3 * heads * 64), generator=g) * 1.5).to(torch.bfloat16).to(DEV)
+    cu = torch.tensor([0] + list(np.cumsum(lengths)), dtype=torch.int32, device=DEV)
+    ops.set_option("attention_impl", impl)
+    try:
+        out = ops.attention(qkv, cu, max(lengths), heads, half_window)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option("attention_impl", 1)
+    ref = _attention_ref(qkv, lengths, heads, half_window)
+    err = (out.double() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all()
+    # bf16 output rounding alone is 2^-9 relative; scale the bound with the magnitude of the outputs
+    tol = 6e-3 * max(1.0, ref.abs().max().item())
+    assert err < tol, f"attention impl={impl} window={half_window}: max err {err:.3e} (tol {tol:.3e})"
+
+
 def test_rope_and_geglu_unfused():
     hidden, m, inter = 128, 500, 256
     cos, sin = rope_table(1024, 64, 10000.0)
