@@ -70,32 +70,46 @@ int get_encode_fn(EncodeTiledFn* out) {
   return OPV_OK;
 }
 
-// 2D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols] with 128 B swizzle.
-int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2D row-major [rows, cols] tensor, box = [box_rows, 128 B of columns] with 128 B swizzle
+// (64 bf16 or 32 fp32 columns per box row).
+int make_tmap_2d(CUtensorMap* map, const void* ptr, bool f32, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn encode;
   if (int rc = get_encode_fn(&encode)) return rc;
+  const uint64_t elt = f32 ? 4 : 2;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(OPV_ERR_INVALID_ARGUMENT, "TMA base not 16 B aligned");
-  if (cols % 8 != 0) return fail(OPV_ERR_INVALID_ARGUMENT, "TMA row pitch must be a multiple of 16 B");
+  if ((cols * elt) % 16 != 0) return fail(OPV_ERR_INVALID_ARGUMENT, "TMA row pitch must be a multiple of 16 B");
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(opv::kGemmBlockK), box_rows};
+  cuuint64_t strides[1] = {cols * elt};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elt), box_rows};
   cuuint32_t elem[2] = {1, 1};
-  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, elem,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                      const_cast<void*>(ptr), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(OPV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return OPV_OK;
+}
+int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  return make_tmap_2d(map, ptr, false, rows, cols, box_rows);
 }
 
 int g_num_sms = 0;
 bool g_attrs_set = false;
 // bf16 attention kernel: 0 = mma.sync v1, 1 = tcgen05 with P in TMEM (default), 2 = tcgen05 with P in smem
 int g_attention_impl = 1;
+// bf16 GEMM with N % 256 == 0: 1 = CTA-pair kernel (cta_group::2, 256 x 256 tiles), 0 = single-CTA kernel
+int g_gemm_pair = 1;
 
 template <int BLOCK_N, int EPI>
 int set_gemm_attr() {
   OPV_CUDA(cudaFuncSetAttribute(opv::gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, opv::GemmSmemLayout<BLOCK_N>::kTotal));
+  return OPV_OK;
+}
+
+template <int EPI>
+int set_gemm_pair_attr() {
+  OPV_CUDA(cudaFuncSetAttribute(opv::gemm_bf16_tcgen05_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                opv::GemmPairSmemLayout::kTotal));
   return OPV_OK;
 }
 
@@ -116,6 +130,10 @@ int ensure_device_setup() {
   if (int rc = set_gemm_attr<128, opv::kEpiStore>()) return rc;
   if (int rc = set_gemm_attr<128, opv::kEpiRope>()) return rc;
   if (int rc = set_gemm_attr<128, opv::kEpiResidual>()) return rc;
+  if (int rc = set_gemm_pair_attr<opv::kEpiStore>()) return rc;
+  if (int rc = set_gemm_pair_attr<opv::kEpiRope>()) return rc;
+  if (int rc = set_gemm_pair_attr<opv::kEpiResidual>()) return rc;
+  if (int rc = set_gemm_pair_attr<opv::kEpiGeglu>()) return rc;
   OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 opv::FaSmemLayout<true>::kTotal));
   OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -125,13 +143,27 @@ int ensure_device_setup() {
 }
 
 template <int BLOCK_N, int EPI>
-int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const opv::GemmEpilogueArgs& ep, int64_t M,
-                   int N, int K, cudaStream_t stream) {
+int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_c,
+                   const opv::GemmEpilogueArgs& ep, int64_t M, int N, int K, cudaStream_t stream) {
   const int64_t tiles = ((M + opv::kGemmBlockM - 1) / opv::kGemmBlockM) * (N / BLOCK_N);
   const int grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
   opv::gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>
-      <<<grid, opv::kGemmThreads, opv::GemmSmemLayout<BLOCK_N>::kTotal, stream>>>(tm_a, tm_b, ep, (int)M, N, K);
+      <<<grid, opv::gemm_threads(EPI), opv::GemmSmemLayout<BLOCK_N>::kTotal, stream>>>(tm_a, tm_b, tm_c, ep, (int)M, N,
+                                                                                       K);
   OPV_LAUNCH_CHECK("gemm_bf16_tcgen05_kernel");
+  return OPV_OK;
+}
+
+template <int EPI>
+int launch_gemm_pair(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_c,
+                     const opv::GemmEpilogueArgs& ep, int64_t M, int N, int K, cudaStream_t stream) {
+  const int64_t tiles = ((M + 2 * opv::kGemmBlockM - 1) / (2 * opv::kGemmBlockM)) * (N / 256);
+  const int max_clusters = g_num_sms / 2;
+  const int clusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
+  opv::gemm_bf16_tcgen05_pair_kernel<EPI>
+      <<<2 * clusters, opv::gemm_threads(EPI), opv::GemmPairSmemLayout::kTotal, stream>>>(tm_a, tm_b, tm_c, ep, (int)M,
+                                                                                          N, K);
+  OPV_LAUNCH_CHECK("gemm_bf16_tcgen05_pair_kernel");
   return OPV_OK;
 }
 
@@ -142,30 +174,42 @@ int gemm_block_n(int N, int epi) {
   return 0;
 }
 
-// A: [M, K] bf16 activations, W: [N, K] bf16 weight (tensor map with box rows = BLOCK_N)
-int gemm_bf16(int epi, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const opv::GemmEpilogueArgs& ep, int64_t M,
-              int N, int K, cudaStream_t stream) {
+// A: [M, K] bf16 activations, W: [N, K] bf16 weight (tensor map with box rows = BLOCK_N), C through tm_c:
+// bf16 [M, N] (STORE/ROPE) or [M, N/2] (GEGLU) with a 64-column box, fp32 [M, N] (RESIDUAL) with a 32-column box.
+// pair: W's tensor map was built with a 128-row box (half tile per CTA) for the CTA-pair kernel.
+int gemm_bf16(int epi, bool pair, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_c,
+              const opv::GemmEpilogueArgs& ep, int64_t M, int N, int K, cudaStream_t stream) {
   if (M <= 0) return OPV_OK;
   if (M > 0x7fffff00LL) return fail(OPV_ERR_UNSUPPORTED, "M = %lld rows exceeds the int32 tile range", (long long)M);
   if (K % opv::kGemmBlockK != 0) return fail(OPV_ERR_UNSUPPORTED, "K = %d must be a multiple of 64", K);
   const int bn = gemm_block_n(N, epi);
   if (bn == 0) return fail(OPV_ERR_UNSUPPORTED, "N = %d must be a multiple of 128 (256 for GeGLU)", N);
-  if (bn == 256) {
+  if (bn == 256 && pair) {
     switch (epi) {
-      case opv::kEpiStore: return launch_gemm_tc<256, opv::kEpiStore>(tm_a, tm_b, ep, M, N, K, stream);
-      case opv::kEpiRope: return launch_gemm_tc<256, opv::kEpiRope>(tm_a, tm_b, ep, M, N, K, stream);
-      case opv::kEpiResidual: return launch_gemm_tc<256, opv::kEpiResidual>(tm_a, tm_b, ep, M, N, K, stream);
-      case opv::kEpiGeglu: return launch_gemm_tc<256, opv::kEpiGeglu>(tm_a, tm_b, ep, M, N, K, stream);
+      case opv::kEpiStore: return launch_gemm_pair<opv::kEpiStore>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
+      case opv::kEpiRope: return launch_gemm_pair<opv::kEpiRope>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
+      case opv::kEpiResidual: return launch_gemm_pair<opv::kEpiResidual>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
+      case opv::kEpiGeglu: return launch_gemm_pair<opv::kEpiGeglu>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
+    }
+  } else if (bn == 256) {
+    switch (epi) {
+      case opv::kEpiStore: return launch_gemm_tc<256, opv::kEpiStore>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
+      case opv::kEpiRope: return launch_gemm_tc<256, opv::kEpiRope>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
+      case opv::kEpiResidual: return launch_gemm_tc<256, opv::kEpiResidual>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
+      case opv::kEpiGeglu: return launch_gemm_tc<256, opv::kEpiGeglu>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
     }
   } else {
     switch (epi) {
-      case opv::kEpiStore: return launch_gemm_tc<128, opv::kEpiStore>(tm_a, tm_b, ep, M, N, K, stream);
-      case opv::kEpiRope: return launch_gemm_tc<128, opv::kEpiRope>(tm_a, tm_b, ep, M, N, K, stream);
-      case opv::kEpiResidual: return launch_gemm_tc<128, opv::kEpiResidual>(tm_a, tm_b, ep, M, N, K, stream);
+      case opv::kEpiStore: return launch_gemm_tc<128, opv::kEpiStore>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
+      case opv::kEpiRope: return launch_gemm_tc<128, opv::kEpiRope>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
+      case opv::kEpiResidual: return launch_gemm_tc<128, opv::kEpiResidual>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
     }
   }
   return fail(OPV_ERR_INVALID_ARGUMENT, "unknown epilogue %d", epi);
 }
+
+// rows of W per TMA box: the CTA-pair kernel loads half of the 256-row tile per CTA
+inline int weight_box_rows(int bn, bool pair) { return (bn == 256 && pair) ? 128 : bn; }
 
 int gemm_f32(bool accumulate, const float* a, const float* w, float* c, int64_t M, int N, int K, int64_t ldc,
              cudaStream_t stream) {
@@ -274,6 +318,7 @@ struct opv_engine {
   opv_weights w;
   std::vector<opv_layer_weights> layers;
   std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_wi, tm_wo2;  // bf16 mode only
+  bool gemm_pair = true;                                   // CTA-pair GEMM kernel for the 256-wide tiles
   int device;
   size_t elt;  // bytes per operand element
 };
@@ -357,6 +402,7 @@ int opv_create(const opv_config* cfg, const opv_weights* w, int device, opv_hand
   e->w = *w;
   e->device = device;
   e->elt = cfg->dtype == OPV_DTYPE_BF16 ? 2 : 4;
+  e->gemm_pair = g_gemm_pair != 0;
   e->layers.assign(w->h_layers, w->h_layers + cfg->num_layers);
   e->w.h_layers = e->layers.data();
   const int H = cfg->hidden_size, I = cfg->intermediate_size;
@@ -383,10 +429,11 @@ int opv_create(const opv_config* cfg, const opv_weights* w, int device, opv_hand
         delete e;
         return fail(OPV_ERR_UNSUPPORTED, "projection widths (3H=%d, H=%d, 2I=%d) do not tile", 3 * H, H, 2 * I);
       }
-      rc = rc ? rc : make_tmap_bf16(&e->tm_wqkv[l], lw.d_wqkv, 3 * H, H, bn_qkv);
-      rc = rc ? rc : make_tmap_bf16(&e->tm_wo[l], lw.d_wo, H, H, bn_h);
-      rc = rc ? rc : make_tmap_bf16(&e->tm_wi[l], lw.d_wi, 2 * I, H, bn_wi);
-      rc = rc ? rc : make_tmap_bf16(&e->tm_wo2[l], lw.d_wo2, H, I, bn_h);
+      const bool pair = e->gemm_pair;
+      rc = rc ? rc : make_tmap_bf16(&e->tm_wqkv[l], lw.d_wqkv, 3 * H, H, weight_box_rows(bn_qkv, pair));
+      rc = rc ? rc : make_tmap_bf16(&e->tm_wo[l], lw.d_wo, H, H, weight_box_rows(bn_h, pair));
+      rc = rc ? rc : make_tmap_bf16(&e->tm_wi[l], lw.d_wi, 2 * I, H, weight_box_rows(bn_wi, pair));
+      rc = rc ? rc : make_tmap_bf16(&e->tm_wo2[l], lw.d_wo2, H, I, weight_box_rows(bn_h, pair));
       if (rc) {
         delete e;
         return rc;
@@ -447,8 +494,10 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
   if (c.dtype == OPV_DTYPE_BF16) {
     using bf16 = __nv_bfloat16;
     const bool fused = c.fuse_epilogues != 0;
-    CUtensorMap tm_x, tm_attn, tm_act, tm_qkv;
-    if ((rc = make_tmap_bf16(&tm_qkv, qkv, T, 3 * H, opv::kFaBlockM))) return rc;
+    CUtensorMap tm_x, tm_attn, tm_act, tm_qkv, tm_h, tm_u;
+    if ((rc = make_tmap_bf16(&tm_qkv, qkv, T, 3 * H, opv::kFaBlockM))) return rc;  // GEMM store + attention loads
+    if ((rc = make_tmap_2d(&tm_h, h, true, T, H, opv::kGemmBlockM))) return rc;     // residual reduce-add
+    if (!fused && (rc = make_tmap_bf16(&tm_u, u, T, 2 * I, opv::kGemmBlockM))) return rc;
     if ((rc = make_tmap_bf16(&tm_x, x, T, H, opv::kGemmBlockM))) return rc;
     if ((rc = make_tmap_bf16(&tm_attn, attn, T, H, opv::kGemmBlockM))) return rc;
     if ((rc = make_tmap_bf16(&tm_act, act, T, I, opv::kGemmBlockM))) return rc;
@@ -467,12 +516,12 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       }
       if (rc) return rc;
       opv::GemmEpilogueArgs ep{};
-      ep.c = qkv, ep.ldc = 3 * H, ep.pos = pos, ep.rope_cols = 2 * H;
+      ep.pos = pos, ep.rope_cols = 2 * H;
       ep.cos = global ? e->w.d_rope_cos_global : e->w.d_rope_cos_local;
       ep.sin = global ? e->w.d_rope_sin_global : e->w.d_rope_sin_local;
       {
         LaunchScope sc(e, stream, OPV_PROF_GEMM_QKV);
-        rc = gemm_bf16(fused ? opv::kEpiRope : opv::kEpiStore, tm_x, e->tm_wqkv[l], ep, T, 3 * H, H, stream);
+        rc = gemm_bf16(fused ? opv::kEpiRope : opv::kEpiStore, e->gemm_pair, tm_x, e->tm_wqkv[l], tm_qkv, ep, T, 3 * H, H, stream);
       }
       if (rc) return rc;
       if (!fused) {
@@ -487,10 +536,9 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       }
       if (rc) return rc;
       opv::GemmEpilogueArgs er{};
-      er.c = h, er.ldc = H;
       {
         LaunchScope sc(e, stream, OPV_PROF_GEMM_WO);
-        rc = gemm_bf16(opv::kEpiResidual, tm_attn, e->tm_wo[l], er, T, H, H, stream);
+        rc = gemm_bf16(opv::kEpiResidual, e->gemm_pair, tm_attn, e->tm_wo[l], tm_h, er, T, H, H, stream);
       }
       if (rc) return rc;
       {
@@ -500,15 +548,13 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       if (rc) return rc;
       if (fused) {
         opv::GemmEpilogueArgs eg{};
-        eg.c = act, eg.ldc = I;
         LaunchScope sc(e, stream, OPV_PROF_GEMM_WI);
-        rc = gemm_bf16(opv::kEpiGeglu, tm_x, e->tm_wi[l], eg, T, 2 * I, H, stream);
+        rc = gemm_bf16(opv::kEpiGeglu, e->gemm_pair, tm_x, e->tm_wi[l], tm_act, eg, T, 2 * I, H, stream);
       } else {
         opv::GemmEpilogueArgs es{};
-        es.c = u, es.ldc = 2 * I;
         {
           LaunchScope sc(e, stream, OPV_PROF_GEMM_WI);
-          rc = gemm_bf16(opv::kEpiStore, tm_x, e->tm_wi[l], es, T, 2 * I, H, stream);
+          rc = gemm_bf16(opv::kEpiStore, e->gemm_pair, tm_x, e->tm_wi[l], tm_u, es, T, 2 * I, H, stream);
         }
         if (rc) return rc;
         LaunchScope sc(e, stream, OPV_PROF_MISC);
@@ -518,7 +564,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       if (rc) return rc;
       {
         LaunchScope sc(e, stream, OPV_PROF_GEMM_WO2);
-        rc = gemm_bf16(opv::kEpiResidual, tm_act, e->tm_wo2[l], er, T, H, I, stream);
+        rc = gemm_bf16(opv::kEpiResidual, e->gemm_pair, tm_act, e->tm_wo2[l], tm_h, er, T, H, I, stream);
       }
       if (rc) return rc;
     }
@@ -675,16 +721,17 @@ int opv_op_gemm(int32_t dtype, int32_t epilogue, const void* d_a, const void* d_
   if (m <= 0) return OPV_OK;
   const int bn = gemm_block_n(n, epilogue);
   if (bn == 0) return fail(OPV_ERR_UNSUPPORTED, "N = %d does not tile for epilogue %d", n, epilogue);
-  CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_a, tm_b, tm_c;
   if (int rc = make_tmap_bf16(&tm_a, d_a, m, k, opv::kGemmBlockM)) return rc;
-  if (int rc = make_tmap_bf16(&tm_b, d_w, n, k, bn)) return rc;
+  const bool pair = g_gemm_pair != 0;
+  if (int rc = make_tmap_bf16(&tm_b, d_w, n, k, weight_box_rows(bn, pair))) return rc;
+  const bool c_f32 = epilogue == OPV_EPI_RESIDUAL;
+  if (int rc = make_tmap_2d(&tm_c, d_c, c_f32, m, epilogue == OPV_EPI_GEGLU ? n / 2 : n, opv::kGemmBlockM)) return rc;
   opv::GemmEpilogueArgs ep{};
-  ep.c = d_c;
-  ep.ldc = (epilogue == OPV_EPI_GEGLU) ? n / 2 : n;
   ep.pos = d_pos, ep.cos = d_cos, ep.sin = d_sin, ep.rope_cols = 2 * hidden_size;
   if (epilogue == OPV_EPI_ROPE && (!d_pos || !d_cos || !d_sin || n != 3 * hidden_size))
     return fail(OPV_ERR_INVALID_ARGUMENT, "ROPE epilogue needs pos/cos/sin and N == 3 * hidden_size");
-  return gemm_bf16(epilogue, tm_a, tm_b, ep, m, n, k, stream);
+  return gemm_bf16(epilogue, pair, tm_a, tm_b, tm_c, ep, m, n, k, stream);
 }
 
 int opv_op_layernorm(int32_t dtype, const float* d_h, const float* d_w, void* d_out, int64_t m, int32_t hidden,
@@ -723,6 +770,10 @@ int opv_set_option(const char* name, int64_t value) {
   if (strcmp(name, "attention_impl") == 0) {
     if (value < 0 || value > 2) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_impl must be 0, 1 or 2");
     g_attention_impl = static_cast<int>(value);
+    return OPV_OK;
+  }
+  if (strcmp(name, "gemm_pair") == 0) {
+    g_gemm_pair = value != 0;
     return OPV_OK;
   }
   return fail(OPV_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);

@@ -2,17 +2,21 @@
 //   C = epilogue(A[M,K] . W[N,K]^T),  A = activations (K-major), W = nn.Linear weight (K-major)
 //
 // Persistent, warp-specialised CTA (one per SM):
-//   warp 0      TMA producer   cp.async.bulk.tensor 2D tiles (128B swizzle) -> 4/6-stage smem ring
-//   warp 1      MMA issuer     one lane issues tcgen05.mma (128 x BLOCK_N x 16), accumulators in TMEM,
-//                              double-buffered (2 x BLOCK_N fp32 columns) so the epilogue of tile i
-//                              overlaps the mainloop of tile i+1
-//   warps 2..5  epilogue       tcgen05.ld TMEM -> registers -> fused op -> global
+//   warp 0        TMA producer   cp.async.bulk.tensor 2D tiles (128B swizzle) -> 4/6-stage smem ring
+//   warp 1        MMA issuer     one lane issues tcgen05.mma (128 x BLOCK_N x 16), accumulators in TMEM,
+//                                double-buffered (2 x BLOCK_N fp32 columns) so the epilogue of tile i
+//                                overlaps the mainloop of tile i+1
+//   warps 2..5    epilogue group 0   tcgen05.ld TMEM -> registers -> fused op -> swizzled smem staging
+//   (warps 6..9)  epilogue group 1   tile -> ONE TMA store (or TMA reduce-add) per 128-row x 128-byte chunk
+// All global traffic goes through TMA: the r1a profile showed the per-thread row stores of the first
+// version (32 different 128 B lines per warp instruction) bound by L1TEX, not by HBM or the tensor pipe.
 // Fused epilogues (SURVEY.md section 7 hard part 2: the H=512 GEMMs are HBM-bound unless the
 // elementwise work rides in the epilogue):
 //   STORE     C bf16
 //   ROPE      rotate-half RoPE on the q,k column thirds with per-row positions (HF:205-228)
-//   RESIDUAL  R(fp32) += acc                                    (HF:340-341)
-//   GEGLU     C[:, j] = gelu_erf(acc[:, in_j]) * acc[:, gate_j]  (HF:90-91), W rows interleaved per 128
+//   RESIDUAL  R(fp32) += acc, performed in L2 by cp.reduce.async.bulk.tensor .add.f32  (HF:340-341)
+//   GEGLU     C[:, j] = gelu_erf(acc[:, in_j]) * acc[:, gate_j]  (HF:90-91), W rows interleaved per 128;
+//             two epilogue groups (8 warps) because erf makes this the heaviest epilogue
 #pragma once
 
 #include "common.cuh"
@@ -21,14 +25,15 @@ namespace opv {
 
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kGemmThreads = 192;
 constexpr int kUmmaK = 16;
+constexpr int kGemmChunkBytes = 128 * 128;  // staging chunk: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
 
 enum : int { kEpiStore = 0, kEpiRope = 1, kEpiResidual = 2, kEpiGeglu = 3 };
 
+__host__ __device__ constexpr int gemm_epi_groups(int epi) { return epi == kEpiGeglu ? 2 : 1; }
+__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 128 * gemm_epi_groups(epi); }
+
 struct GemmEpilogueArgs {
-  void* c;             // STORE/ROPE/GEGLU: bf16 [M, ldc]; RESIDUAL: fp32 [M, ldc] (read-modify-write)
-  int64_t ldc;         // row pitch of c in elements
   const int32_t* pos;  // ROPE: [M] position of each row inside its sequence
   const float* cos;    // ROPE: [max_pos, 32]
   const float* sin;    // ROPE: [max_pos, 32]
@@ -41,42 +46,75 @@ struct GemmSmemLayout {
   static constexpr int kStageB = BLOCK_N * kGemmBlockK * 2;
   static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
   static constexpr int kTileBytes = kStages * (kStageA + kStageB);
+  static constexpr int kStagingBytes = 2 * kGemmChunkBytes;  // 2 buffers (1 group) or 1 buffer x 2 groups
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = kTileBytes + kBarrierBytes + 1024;  // + slack for the 1024 B alignment
-  static constexpr int kTmemCols = 2 * BLOCK_N;                     // 512 or 256: power of two >= 32
+  static constexpr int kTotal = kTileBytes + kStagingBytes + kBarrierBytes + 1024;  // + 1024 B alignment slack
+  static constexpr int kTmemCols = 2 * BLOCK_N;                                      // 512 or 256
 };
 
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
+// One 128 B row of the staging chunk, 16 B pieces XOR-swizzled exactly like TMA's SWIZZLE_128B.
+__device__ __forceinline__ void staging_write_row(uint8_t* buf, int r, const uint32_t (&w)[32]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-    d4[i] = u;
-  }
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<uint4*>(buf + r * 128 + ((g ^ (r & 7)) << 4)) =
+        make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
 }
 
-template <int BLOCK_N, int EPI>
-__device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogueArgs& ep, uint32_t taddr, int64_t row, int M,
-                                                   int n0, int n_blk) {
-  const bool row_ok = row < M;
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Epilogue-group state: which staging buffer is next and how many buffers the group owns.
+template <int NBUF>
+struct StagingRing {
+  uint8_t* base;
+  int next = 0;
+  int bar_id;
+  bool leader;  // the one thread that issues the TMA stores of this group
+
+  // returns the buffer to fill; on return the TMA store that last read it has finished reading
+  __device__ __forceinline__ uint8_t* acquire() {
+    if (leader) tma_store_wait_read<NBUF - 1>();
+    named_bar_sync(bar_id, 128);
+    return base + next * kGemmChunkBytes;
+  }
+  // all 128 threads call after writing their row; the leader then issues `op(buf)`
+  template <typename Issue>
+  __device__ __forceinline__ void release(uint8_t* buf, Issue&& issue) {
+    fence_proxy_async_smem();
+    named_bar_sync(bar_id, 128);
+    if (leader) {
+      issue(buf);
+      tma_store_commit();
+    }
+    next = (next + 1 == NBUF) ? 0 : next + 1;
+  }
+};
+
+template <int BLOCK_N, int EPI, int NBUF>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogueArgs& ep, const CUtensorMap* tm_c,
+                                                   StagingRing<NBUF>& ring, uint32_t taddr, int r_tile, int64_t row,
+                                                   int M, int m_blk, int n_blk, int group) {
+  const int row0 = m_blk * kGemmBlockM;
   if constexpr (EPI == kEpiStore) {
-    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.c) + row * ep.ldc + n0;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      float v[32];
-      tmem_ld_32x32(taddr + c * 32, v);
-      if (row_ok) store_bf16x32(crow + c * 32, v);
+    for (int c = 0; c < BLOCK_N / 64; ++c) {
+      float lo[32], hi[32];
+      tmem_ld_32x32(taddr + c * 64, lo);
+      tmem_ld_32x32(taddr + c * 64 + 32, hi);
+      uint32_t w[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(lo[2 * i], lo[2 * i + 1]), w[16 + i] = pack_bf16x2(hi[2 * i], hi[2 * i + 1]);
+      uint8_t* buf = ring.acquire();
+      staging_write_row(buf, r_tile, w);
+      const int col0 = n_blk * BLOCK_N + c * 64;
+      ring.release(buf, [&](uint8_t* b) { tma_store_2d(tm_c, b, col0, row0); });
     }
   } else if constexpr (EPI == kEpiRope) {
-    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.c) + row * ep.ldc + n0;
-    const bool rotate = n0 < ep.rope_cols;  // tile-uniform: rope_cols (2H) is a multiple of BLOCK_N
+    const bool rotate = n_blk * BLOCK_N < ep.rope_cols;  // tile-uniform: rope_cols (2H) is a multiple of BLOCK_N
     float cs[32], sn[32];
     if (rotate) {
-      const int p = row_ok ? ep.pos[row] : 0;
+      const int p = row < M ? ep.pos[row] : 0;
       const float4* c4 = reinterpret_cast<const float4*>(ep.cos + static_cast<int64_t>(p) * 32);
       const float4* s4 = reinterpret_cast<const float4*>(ep.sin + static_cast<int64_t>(p) * 32);
 #pragma unroll
@@ -87,7 +125,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogueArgs& ep, u
       }
     }
 #pragma unroll 1
-    for (int hd = 0; hd < BLOCK_N / 64; ++hd) {  // one 64-wide head per iteration
+    for (int hd = 0; hd < BLOCK_N / 64; ++hd) {  // one 64-wide head per chunk
       float lo[32], hi[32];
       tmem_ld_32x32(taddr + hd * 64, lo);
       tmem_ld_32x32(taddr + hd * 64 + 32, hi);
@@ -99,52 +137,60 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogueArgs& ep, u
           hi[i] = b * cs[i] + a * sn[i];  // second half
         }
       }
-      if (row_ok) {
-        store_bf16x32(crow + hd * 64, lo);
-        store_bf16x32(crow + hd * 64 + 32, hi);
-      }
+      uint32_t w[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(lo[2 * i], lo[2 * i + 1]), w[16 + i] = pack_bf16x2(hi[2 * i], hi[2 * i + 1]);
+      uint8_t* buf = ring.acquire();
+      staging_write_row(buf, r_tile, w);
+      const int col0 = n_blk * BLOCK_N + hd * 64;
+      ring.release(buf, [&](uint8_t* b) { tma_store_2d(tm_c, b, col0, row0); });
     }
   } else if constexpr (EPI == kEpiResidual) {
-    float* rrow = reinterpret_cast<float*>(ep.c) + row * ep.ldc + n0;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      float v[32];
-      tmem_ld_32x32(taddr + c * 32, v);
-      if (row_ok) {
-        float4* r4 = reinterpret_cast<float4*>(rrow + c * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 r = r4[i];
-          r.x += v[4 * i + 0], r.y += v[4 * i + 1], r.z += v[4 * i + 2], r.w += v[4 * i + 3];
-          r4[i] = r;
-        }
-      }
+    for (int c = 0; c < BLOCK_N / 32; ++c) {  // 32 fp32 columns = 128 B per row
+      uint32_t w[32];
+      tmem_ld_32x32_raw(taddr + c * 32, w);
+      uint8_t* buf = ring.acquire();
+      staging_write_row(buf, r_tile, w);
+      const int col0 = n_blk * BLOCK_N + c * 32;
+      ring.release(buf, [&](uint8_t* b) { tma_reduce_add_2d(tm_c, b, col0, row0); });
     }
   } else {  // kEpiGeglu: tile columns [0,128) = "input", [128,256) = "gate" of the same 128 features
     static_assert(EPI != kEpiGeglu || BLOCK_N == 256, "GeGLU epilogue needs BLOCK_N = 256");
-    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.c) + row * ep.ldc + n_blk * 128;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float a[32], g[32];
-      tmem_ld_32x32(taddr + c * 32, a);
-      tmem_ld_32x32(taddr + 128 + c * 32, g);
+    // group g produces output columns [64g, 64g + 64) of this tile's 128
+    uint32_t w[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) a[i] = gelu_erf(a[i]) * g[i];
-      if (row_ok) store_bf16x32(crow + c * 32, a);
+    for (int half = 0; half < 2; ++half) {
+      float a[32], g[32];
+      tmem_ld_32x32(taddr + group * 64 + half * 32, a);
+      tmem_ld_32x32(taddr + 128 + group * 64 + half * 32, g);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        w[16 * half + i] = pack_bf16x2(gelu_erf(a[2 * i]) * g[2 * i], gelu_erf(a[2 * i + 1]) * g[2 * i + 1]);
     }
+    uint8_t* buf = ring.acquire();
+    staging_write_row(buf, r_tile, w);
+    const int col0 = n_blk * 128 + group * 64;
+    ring.release(buf, [&](uint8_t* b) { tma_store_2d(tm_c, b, col0, row0); });
   }
 }
 
+// tm_c: STORE/ROPE/GEGLU bf16 [M, ldc] with a 64-column x 128-row box; RESIDUAL fp32 [M, N] with a
+// 32-column x 128-row box (both SWIZZLE_128B).  TMA clips rows >= M.
 template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                         const GemmEpilogueArgs ep, const int M, const int N, const int K) {
+                         const __grid_constant__ CUtensorMap tm_c, const GemmEpilogueArgs ep, const int M,
+                         const int N, const int K) {
   using L = GemmSmemLayout<BLOCK_N>;
+  constexpr int kGroups = gemm_epi_groups(EPI);
+  constexpr int kBufsPerGroup = 2 / kGroups;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + L::kStages * L::kStageA;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes);
+  uint8_t* staging = smem + L::kTileBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes + L::kStagingBytes);
   uint64_t* empty_bar = full_bar + L::kStages;
   uint64_t* tmem_full = empty_bar + L::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -160,6 +206,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < L::kStages; ++s) {
@@ -168,7 +215,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], 4 * kGroups);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -232,27 +279,193 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
   } else {
     // ------------------------------ epilogue warps ----------------------------
-    const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int quarter = warp & 3;         // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int group = (warp - 2) >> 2;    // 0 (warps 2..5) or 1 (warps 6..9)
+    const int r_tile = quarter * 32 + lane;
+    StagingRing<kBufsPerGroup> ring;
+    ring.base = staging + group * kBufsPerGroup * kGemmChunkBytes;
+    ring.bar_id = 1 + group;
+    ring.leader = ((warp - 2) & 3) == 0 && lane == 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int64_t row = static_cast<int64_t>(m_blk) * kGemmBlockM + quarter * 32 + lane;
+      const int64_t row = static_cast<int64_t>(m_blk) * kGemmBlockM + r_tile;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-      gemm_epilogue_tile<BLOCK_N, EPI>(ep, taddr, row, M, n_blk * BLOCK_N, n_blk);
+      gemm_epilogue_tile<BLOCK_N, EPI>(ep, &tm_c, ring, taddr, r_tile, row, M, m_blk, n_blk, group);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (ring.leader) tma_store_wait_all();  // smem must outlive the bulk stores that read it
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, L::kTmemCols);
+}
+
+// --------------------------------------------------------------------------------------------------
+// CTA-pair version (cta_group::2), BLOCK_N = 256: a 2-CTA cluster on one TPC computes a 256 x 256 tile.
+// Each CTA stages its own 128 rows of A and HALF of the W tile (128 of the 256 rows) per k-block, so the
+// L2 -> SM operand traffic per FLOP drops by a third against the single-CTA kernel (which the r1c
+// measurements showed capped near 1 PFLOP/s by L2 bandwidth: 384 KB of operands per 33.5 MFLOP tile).
+// The even CTA's warp 1 issues tcgen05.mma.cta_group::2 (M = 256) for the pair; TMA bytes of both CTAs
+// are counted on the even CTA's full barrier; tcgen05.commit multicasts the smem-slot / accumulator
+// hand-offs to both CTAs; each CTA's epilogue drains its own 128 TMEM lanes exactly as above.
+// --------------------------------------------------------------------------------------------------
+struct GemmPairSmemLayout {
+  static constexpr int kStageA = kGemmBlockM * kGemmBlockK * 2;  // 16 KB: this CTA's 128 rows of A
+  static constexpr int kStageB = 128 * kGemmBlockK * 2;          // 16 KB: this CTA's half of the 256 W rows
+  static constexpr int kStages = 6;
+  static constexpr int kTileBytes = kStages * (kStageA + kStageB);
+  static constexpr int kStagingBytes = 2 * kGemmChunkBytes;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = kTileBytes + kStagingBytes + kBarrierBytes + 1024;
+  static constexpr int kTmemCols = 512;  // two 256-column accumulators per CTA
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EPI), 1)
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                              const __grid_constant__ CUtensorMap tm_c, const GemmEpilogueArgs ep, const int M,
+                              const int N, const int K) {
+  using L = GemmPairSmemLayout;
+  constexpr int BLOCK_N = 256;
+  constexpr int kGroups = gemm_epi_groups(EPI);
+  constexpr int kBufsPerGroup = 2 / kGroups;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + L::kStages * L::kStageA;
+  uint8_t* staging = smem + L::kTileBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes + L::kStagingBytes);
+  uint64_t* empty_bar = full_bar + L::kStages;
+  uint64_t* tmem_full = empty_bar + L::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = static_cast<int>(cluster_ctarank());  // 0 = leader (issues the MMAs)
+  const int num_pairs_m = (M + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM);
+  const int num_n = N / BLOCK_N;
+  const int num_tiles = num_pairs_m * num_n;  // 256 x 256 tiles
+  const int num_kb = K / kGemmBlockK;
+  const int first_tile = static_cast<int>(cluster_id_x());
+  const int tile_step = static_cast<int>(cluster_nctaid_x());
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_c);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < L::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader's producer arrives (expect_tx covers both CTAs' bytes)
+      mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit from the leader
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);                  // multicast tcgen05.commit from the leader
+      mbar_init(&tmem_empty[s], 2 * 4 * kGroups);   // epilogue warps of BOTH CTAs (used on the leader only)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, L::kTmemCols);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits of both CTAs visible before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int m_pair = tile / num_n, n_blk = tile % num_n;
+      const int row0 = (m_pair * 2 + cta_rank) * kGemmBlockM;
+      const int wrow0 = n_blk * BLOCK_N + cta_rank * 128;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (L::kStageA + L::kStageB));
+          tma_load_2d_pair(smem_a + stage * L::kStageA, &tm_a, &full_bar[stage], kb * kGemmBlockK, row0);
+          tma_load_2d_pair(smem_b + stage * L::kStageB, &tm_b, &full_bar[stage], kb * kGemmBlockK, wrow0);
+        }
+        __syncwarp();
+        if (++stage == L::kStages) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) --------------
+    if (cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(2 * kGemmBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // both CTAs' epilogues drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);  // both CTAs' TMA bytes have landed
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_base = smem_u32(smem_a + stage * L::kStageA);
+            const uint32_t b_base = smem_u32(smem_b + stage * L::kStageB);
+#pragma unroll
+            for (int k = 0; k < kGemmBlockK / kUmmaK; ++k)
+              umma_bf16_ss_pair(d_tmem, umma_desc_k_sw128(a_base + k * 32), umma_desc_k_sw128(b_base + k * 32), idesc,
+                                (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage], 0b11);                      // slot free in both CTAs
+            if (kb == num_kb - 1) umma_commit_pair(&tmem_full[acc], 0b11);  // accumulators complete in both
+          }
+          __syncwarp();
+          if (++stage == L::kStages) stage = 0, phase ^= 1;
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------ epilogue warps (both CTAs) ----------------
+    const int quarter = warp & 3;
+    const int group = (warp - 2) >> 2;
+    const int r_tile = quarter * 32 + lane;
+    StagingRing<kBufsPerGroup> ring;
+    ring.base = staging + group * kBufsPerGroup * kGemmChunkBytes;
+    ring.bar_id = 1 + group;
+    ring.leader = ((warp - 2) & 3) == 0 && lane == 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int m_pair = tile / num_n, n_blk = tile % num_n;
+      const int m_blk = m_pair * 2 + cta_rank;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int64_t row = static_cast<int64_t>(m_blk) * kGemmBlockM + r_tile;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      gemm_epilogue_tile<BLOCK_N, EPI>(ep, &tm_c, ring, taddr, r_tile, row, M, m_blk, n_blk, group);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_pair_leader(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (ring.leader) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch its smem / TMEM
+  if (warp == 2) tmem_dealloc_pair(tmem_base, L::kTmemCols);
 }
 
 }  // namespace opv

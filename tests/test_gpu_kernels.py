@@ -30,6 +30,14 @@ def _bf16_close(out: torch.Tensor, ref: torch.Tensor, what: str):
     assert bad == 0, f"{what}: {bad} elements out of tolerance, max err {err.max().item():.4e}, ref max {ref.abs().max().item():.3e}"
 
 
+@pytest.fixture(params=[1, 0], ids=["pair", "single"])
+def gemm_kernel(request):
+    """Run the bf16 GEMM tests on both kernels: CTA pair (cta_group::2, default) and single CTA."""
+    ops.set_option("gemm_pair", request.param)
+    yield request.param
+    ops.set_option("gemm_pair", 1)
+
+
 GEMM_SHAPES = [
     (128, 128, 64),
     (128, 256, 64),
@@ -43,7 +51,7 @@ GEMM_SHAPES = [
 
 
 @pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
-def test_gemm_bf16_store(m, n, k):
+def test_gemm_bf16_store(m, n, k, gemm_kernel):
     a = _rand_bf16((m, k), 1)
     w = _rand_bf16((n, k), 2, 0.05)
     out = ops.gemm(a, w)
@@ -53,7 +61,7 @@ def test_gemm_bf16_store(m, n, k):
 
 
 @pytest.mark.parametrize("m,n,k", [(300, 128, 128), (1000, 512, 2048), (4113, 256, 512)])
-def test_gemm_bf16_residual(m, n, k):
+def test_gemm_bf16_residual(m, n, k, gemm_kernel):
     a = _rand_bf16((m, k), 3)
     w = _rand_bf16((n, k), 4, 0.05)
     g = torch.Generator().manual_seed(5)
@@ -80,7 +88,7 @@ def _rope_ref(qkv: torch.Tensor, pos: torch.Tensor, cos: torch.Tensor, sin: torc
 
 
 @pytest.mark.parametrize("m,hidden", [(333, 128), (1500, 256), (2000, 512)])
-def test_gemm_bf16_rope(m, hidden):
+def test_gemm_bf16_rope(m, hidden, gemm_kernel):
     a = _rand_bf16((m, hidden), 6)
     w = _rand_bf16((3 * hidden, hidden), 7, 0.05)
     cos, sin = rope_table(4096, 64, 160000.0)
@@ -94,7 +102,7 @@ def test_gemm_bf16_rope(m, hidden):
 
 
 @pytest.mark.parametrize("m,k,inter", [(300, 128, 128), (1000, 512, 2048), (4113, 256, 1152)])
-def test_gemm_bf16_geglu(m, k, inter):
+def test_gemm_bf16_geglu(m, k, inter, gemm_kernel):
     a = _rand_bf16((m, k), 9)
     wi = _rand_bf16((2 * inter, k), 10, 0.08)
     out = ops.gemm(a, interleave_wi(wi), epilogue=N.EPI_GEGLU)
