@@ -102,14 +102,14 @@ int g_gemm_pair = 1;
 template <int BLOCK_N, int EPI>
 int set_gemm_attr() {
   OPV_CUDA(cudaFuncSetAttribute(opv::gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, opv::GemmSmemLayout<BLOCK_N>::kTotal));
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, opv::GemmSmemLayout<BLOCK_N, EPI>::kTotal));
   return OPV_OK;
 }
 
 template <int EPI>
 int set_gemm_pair_attr() {
   OPV_CUDA(cudaFuncSetAttribute(opv::gemm_bf16_tcgen05_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                opv::GemmPairSmemLayout::kTotal));
+                                opv::GemmPairSmemLayout<EPI>::kTotal));
   return OPV_OK;
 }
 
@@ -148,7 +148,7 @@ int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUten
   const int64_t tiles = ((M + opv::kGemmBlockM - 1) / opv::kGemmBlockM) * (N / BLOCK_N);
   const int grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
   opv::gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>
-      <<<grid, opv::gemm_threads(EPI), opv::GemmSmemLayout<BLOCK_N>::kTotal, stream>>>(tm_a, tm_b, tm_c, ep, (int)M, N,
+      <<<grid, opv::gemm_threads(EPI), opv::GemmSmemLayout<BLOCK_N, EPI>::kTotal, stream>>>(tm_a, tm_b, tm_c, ep, (int)M, N,
                                                                                        K);
   OPV_LAUNCH_CHECK("gemm_bf16_tcgen05_kernel");
   return OPV_OK;
@@ -161,7 +161,7 @@ int launch_gemm_pair(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUt
   const int max_clusters = g_num_sms / 2;
   const int clusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
   opv::gemm_bf16_tcgen05_pair_kernel<EPI>
-      <<<2 * clusters, opv::gemm_threads(EPI), opv::GemmPairSmemLayout::kTotal, stream>>>(tm_a, tm_b, tm_c, ep, (int)M,
+      <<<2 * clusters, opv::gemm_threads(EPI), opv::GemmPairSmemLayout<EPI>::kTotal, stream>>>(tm_a, tm_b, tm_c, ep, (int)M,
                                                                                           N, K);
   OPV_LAUNCH_CHECK("gemm_bf16_tcgen05_pair_kernel");
   return OPV_OK;

@@ -7,7 +7,7 @@
 //                                double-buffered (2 x BLOCK_N fp32 columns) so the epilogue of tile i
 //                                overlaps the mainloop of tile i+1
 //   warps 2..5    epilogue group 0   tcgen05.ld TMEM -> registers -> fused op -> swizzled smem staging
-//   (warps 6..9)  epilogue group 1   tile -> ONE TMA store (or TMA reduce-add) per 128-row x 128-byte chunk
+//   warps 6..9    epilogue group 1   tile -> ONE TMA store (or TMA reduce-add) per 128-row x 128-byte chunk
 // All global traffic goes through TMA: the r1a profile showed the per-thread row stores of the first
 // version (32 different 128 B lines per warp instruction) bound by L1TEX, not by HBM or the tensor pipe.
 // Fused epilogues (SURVEY.md section 7 hard part 2: the H=512 GEMMs are HBM-bound unless the
@@ -16,7 +16,7 @@
 //   ROPE      rotate-half RoPE on the q,k column thirds with per-row positions (HF:205-228)
 //   RESIDUAL  R(fp32) += acc, performed in L2 by cp.reduce.async.bulk.tensor .add.f32  (HF:340-341)
 //   GEGLU     C[:, j] = gelu_erf(acc[:, in_j]) * acc[:, gate_j]  (HF:90-91), W rows interleaved per 128;
-//             two epilogue groups (8 warps) because erf makes this the heaviest epilogue
+//             gelu through the branch-free exp2 form of the Gaussian CDF (common.cuh: gelu_fast)
 #pragma once
 
 #include "common.cuh"
@@ -30,7 +30,9 @@ constexpr int kGemmChunkBytes = 128 * 128;  // staging chunk: 128 rows x 128 B (
 
 enum : int { kEpiStore = 0, kEpiRope = 1, kEpiResidual = 2, kEpiGeglu = 3 };
 
-__host__ __device__ constexpr int gemm_epi_groups(int epi) { return epi == kEpiGeglu ? 2 : 1; }
+// Two epilogue groups (8 warps) for every epilogue: the r1b profile showed the K = 512 GEMMs waiting on a
+// single 4-warp epilogue (tensor pipe 64 % active on Wqkv+RoPE); the groups take alternate 128 B chunks.
+__host__ __device__ constexpr int gemm_epi_groups(int /*epi*/) { return 2; }
 __host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 128 * gemm_epi_groups(epi); }
 
 struct GemmEpilogueArgs {
@@ -40,16 +42,22 @@ struct GemmEpilogueArgs {
   int32_t rope_cols;   // ROPE: output columns < rope_cols (= 2H: q and k) are rotated
 };
 
-template <int BLOCK_N>
+// ROPE epilogue: the cos|sin rows (2 x 128 B) of the tile's 128 tokens are staged in shared memory by
+// coalesced loads (one pipeline stage is given up for the 32 KB); see rope_stage_rows().
+constexpr int kRopeRowBytes = 256;
+__host__ __device__ constexpr int gemm_rope_bytes(int epi) { return epi == kEpiRope ? kGemmBlockM * kRopeRowBytes : 0; }
+
+template <int BLOCK_N, int EPI>
 struct GemmSmemLayout {
   static constexpr int kStageA = kGemmBlockM * kGemmBlockK * 2;
   static constexpr int kStageB = BLOCK_N * kGemmBlockK * 2;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kStages = ((BLOCK_N == 256) ? 4 : 6) - (EPI == kEpiRope ? 1 : 0);
   static constexpr int kTileBytes = kStages * (kStageA + kStageB);
-  static constexpr int kStagingBytes = 2 * kGemmChunkBytes;  // 2 buffers (1 group) or 1 buffer x 2 groups
+  static constexpr int kStagingBytes = 2 * kGemmChunkBytes;  // one buffer per epilogue group
+  static constexpr int kRopeBytes = gemm_rope_bytes(EPI);
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = kTileBytes + kStagingBytes + kBarrierBytes + 1024;  // + 1024 B alignment slack
-  static constexpr int kTmemCols = 2 * BLOCK_N;                                      // 512 or 256
+  static constexpr int kTotal = kTileBytes + kStagingBytes + kRopeBytes + kBarrierBytes + 1024;  // + alignment slack
+  static constexpr int kTmemCols = 2 * BLOCK_N;                                                   // 512 or 256
 };
 
 // One 128 B row of the staging chunk, 16 B pieces XOR-swizzled exactly like TMA's SWIZZLE_128B.
@@ -91,14 +99,33 @@ struct StagingRing {
   }
 };
 
+// ROPE: all 256 epilogue threads copy the cos|sin table rows of the tile's 128 tokens into shared memory.
+// 16 lanes read one token's 256 B (cos row, then sin row) with 16 B loads, so a warp instruction touches 4
+// lines instead of the 32 that "one lane = one token" reads cost (the r1c profile: 8 warps x 16 such loads per
+// head made L1 the limiter of the Wqkv GEMM).  16 B pieces are XOR-swizzled on the low 3 row bits so both
+// this store and the per-row reads of the epilogue are bank-conflict free.
+__device__ __forceinline__ void rope_stage_rows(const GemmEpilogueArgs& ep, uint8_t* rope_cs, int epi_tid, int row0,
+                                                int M) {
+  const int piece = epi_tid & 15;  // 0..7 = cos, 8..15 = sin
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 16 + (epi_tid >> 4);
+    const int64_t row = static_cast<int64_t>(row0) + r;
+    const int p = row < M ? __ldg(ep.pos + row) : 0;
+    const float* src = (piece < 8 ? ep.cos : ep.sin) + static_cast<int64_t>(p) * 32 + (piece & 7) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+    *reinterpret_cast<float4*>(rope_cs + r * kRopeRowBytes + ((piece ^ (r & 7)) << 4)) = v;
+  }
+}
+
 template <int BLOCK_N, int EPI, int NBUF>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogueArgs& ep, const CUtensorMap* tm_c,
-                                                   StagingRing<NBUF>& ring, uint32_t taddr, int r_tile, int64_t row,
-                                                   int M, int m_blk, int n_blk, int group) {
+                                                   StagingRing<NBUF>& ring, const uint8_t* rope_cs, uint32_t taddr,
+                                                   int r_tile, int64_t row, int M, int m_blk, int n_blk, int group) {
   const int row0 = m_blk * kGemmBlockM;
   if constexpr (EPI == kEpiStore) {
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 64; ++c) {
+    for (int c = group; c < BLOCK_N / 64; c += gemm_epi_groups(EPI)) {
       float lo[32], hi[32];
       tmem_ld_32x32(taddr + c * 64, lo);
       tmem_ld_32x32(taddr + c * 64 + 32, hi);
@@ -112,29 +139,24 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogueArgs& ep, c
     }
   } else if constexpr (EPI == kEpiRope) {
     const bool rotate = n_blk * BLOCK_N < ep.rope_cols;  // tile-uniform: rope_cols (2H) is a multiple of BLOCK_N
-    float cs[32], sn[32];
-    if (rotate) {
-      const int p = row < M ? ep.pos[row] : 0;
-      const float4* c4 = reinterpret_cast<const float4*>(ep.cos + static_cast<int64_t>(p) * 32);
-      const float4* s4 = reinterpret_cast<const float4*>(ep.sin + static_cast<int64_t>(p) * 32);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 a = __ldg(c4 + i), b = __ldg(s4 + i);
-        cs[4 * i + 0] = a.x, cs[4 * i + 1] = a.y, cs[4 * i + 2] = a.z, cs[4 * i + 3] = a.w;
-        sn[4 * i + 0] = b.x, sn[4 * i + 1] = b.y, sn[4 * i + 2] = b.z, sn[4 * i + 3] = b.w;
-      }
-    }
+    const uint8_t* cs_row = rope_cs + r_tile * kRopeRowBytes;
 #pragma unroll 1
-    for (int hd = 0; hd < BLOCK_N / 64; ++hd) {  // one 64-wide head per chunk
+    for (int hd = group; hd < BLOCK_N / 64; hd += gemm_epi_groups(EPI)) {  // one 64-wide head per chunk
       float lo[32], hi[32];
       tmem_ld_32x32(taddr + hd * 64, lo);
       tmem_ld_32x32(taddr + hd * 64 + 32, hi);
       if (rotate) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float a = lo[i], b = hi[i];
-          lo[i] = a * cs[i] - b * sn[i];  // t*cos + rotate_half(t)*sin, first half
-          hi[i] = b * cs[i] + a * sn[i];  // second half
+        for (int i = 0; i < 8; ++i) {
+          const float4 c = *reinterpret_cast<const float4*>(cs_row + ((i ^ (r_tile & 7)) << 4));
+          const float4 sn = *reinterpret_cast<const float4*>(cs_row + (((8 + i) ^ (r_tile & 7)) << 4));
+          const float cs_[4] = {c.x, c.y, c.z, c.w}, sn_[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = lo[4 * i + j], b = hi[4 * i + j];
+            lo[4 * i + j] = a * cs_[j] - b * sn_[j];  // t*cos + rotate_half(t)*sin, first half
+            hi[4 * i + j] = b * cs_[j] + a * sn_[j];  // second half
+          }
         }
       }
       uint32_t w[32];
@@ -147,7 +169,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogueArgs& ep, c
     }
   } else if constexpr (EPI == kEpiResidual) {
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {  // 32 fp32 columns = 128 B per row
+    for (int c = group; c < BLOCK_N / 32; c += gemm_epi_groups(EPI)) {  // 32 fp32 columns = 128 B per row
       uint32_t w[32];
       tmem_ld_32x32_raw(taddr + c * 32, w);
       uint8_t* buf = ring.acquire();
@@ -166,7 +188,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogueArgs& ep, c
       tmem_ld_32x32(taddr + 128 + group * 64 + half * 32, g);
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        w[16 * half + i] = pack_bf16x2(gelu_erf(a[2 * i]) * g[2 * i], gelu_erf(a[2 * i + 1]) * g[2 * i + 1]);
+        w[16 * half + i] = pack_bf16x2(gelu_fast(a[2 * i]) * g[2 * i], gelu_fast(a[2 * i + 1]) * g[2 * i + 1]);
     }
     uint8_t* buf = ring.acquire();
     staging_write_row(buf, r_tile, w);
@@ -182,7 +204,7 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const __grid_constant__ CUtensorMap tm_c, const GemmEpilogueArgs ep, const int M,
                          const int N, const int K) {
-  using L = GemmSmemLayout<BLOCK_N>;
+  using L = GemmSmemLayout<BLOCK_N, EPI>;
   constexpr int kGroups = gemm_epi_groups(EPI);
   constexpr int kBufsPerGroup = 2 / kGroups;
   extern __shared__ uint8_t smem_raw[];
@@ -190,7 +212,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + L::kStages * L::kStageA;
   uint8_t* staging = smem + L::kTileBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes + L::kStagingBytes);
+  uint8_t* rope_cs = staging + L::kStagingBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes + L::kStagingBytes + L::kRopeBytes);
   uint64_t* empty_bar = full_bar + L::kStages;
   uint64_t* tmem_full = empty_bar + L::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -290,11 +313,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
+      if constexpr (EPI == kEpiRope) {
+        // stage this tile's cos|sin rows while its mainloop is still running (TMEM is double-buffered)
+        if (n_blk * BLOCK_N < ep.rope_cols) {
+          named_bar_sync(3, 256);  // every epilogue thread is done reading the previous tile's rows
+          rope_stage_rows(ep, rope_cs, threadIdx.x - 64, m_blk * kGemmBlockM, M);
+          named_bar_sync(3, 256);
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int64_t row = static_cast<int64_t>(m_blk) * kGemmBlockM + r_tile;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-      gemm_epilogue_tile<BLOCK_N, EPI>(ep, &tm_c, ring, taddr, r_tile, row, M, m_blk, n_blk, group);
+      gemm_epilogue_tile<BLOCK_N, EPI>(ep, &tm_c, ring, rope_cs, taddr, r_tile, row, M, m_blk, n_blk, group);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -318,14 +349,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 // are counted on the even CTA's full barrier; tcgen05.commit multicasts the smem-slot / accumulator
 // hand-offs to both CTAs; each CTA's epilogue drains its own 128 TMEM lanes exactly as above.
 // --------------------------------------------------------------------------------------------------
+template <int EPI>
 struct GemmPairSmemLayout {
   static constexpr int kStageA = kGemmBlockM * kGemmBlockK * 2;  // 16 KB: this CTA's 128 rows of A
   static constexpr int kStageB = 128 * kGemmBlockK * 2;          // 16 KB: this CTA's half of the 256 W rows
-  static constexpr int kStages = 6;
+  static constexpr int kStages = EPI == kEpiRope ? 5 : 6;
   static constexpr int kTileBytes = kStages * (kStageA + kStageB);
   static constexpr int kStagingBytes = 2 * kGemmChunkBytes;
+  static constexpr int kRopeBytes = gemm_rope_bytes(EPI);
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = kTileBytes + kStagingBytes + kBarrierBytes + 1024;
+  static constexpr int kTotal = kTileBytes + kStagingBytes + kRopeBytes + kBarrierBytes + 1024;
   static constexpr int kTmemCols = 512;  // two 256-column accumulators per CTA
 };
 
@@ -334,7 +367,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EPI), 1
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                               const __grid_constant__ CUtensorMap tm_c, const GemmEpilogueArgs ep, const int M,
                               const int N, const int K) {
-  using L = GemmPairSmemLayout;
+  using L = GemmPairSmemLayout<EPI>;
   constexpr int BLOCK_N = 256;
   constexpr int kGroups = gemm_epi_groups(EPI);
   constexpr int kBufsPerGroup = 2 / kGroups;
@@ -343,7 +376,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + L::kStages * L::kStageA;
   uint8_t* staging = smem + L::kTileBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes + L::kStagingBytes);
+  uint8_t* rope_cs = staging + L::kStagingBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes + L::kStagingBytes + L::kRopeBytes);
   uint64_t* empty_bar = full_bar + L::kStages;
   uint64_t* tmem_full = empty_bar + L::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -449,11 +483,18 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int m_pair = tile / num_n, n_blk = tile % num_n;
       const int m_blk = m_pair * 2 + cta_rank;
+      if constexpr (EPI == kEpiRope) {
+        if (n_blk * BLOCK_N < ep.rope_cols) {
+          named_bar_sync(3, 256);
+          rope_stage_rows(ep, rope_cs, threadIdx.x - 64, m_blk * kGemmBlockM, M);
+          named_bar_sync(3, 256);
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int64_t row = static_cast<int64_t>(m_blk) * kGemmBlockM + r_tile;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-      gemm_epilogue_tile<BLOCK_N, EPI>(ep, &tm_c, ring, taddr, r_tile, row, M, m_blk, n_blk, group);
+      gemm_epilogue_tile<BLOCK_N, EPI>(ep, &tm_c, ring, rope_cs, taddr, r_tile, row, M, m_blk, n_blk, group);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_pair_leader(&tmem_empty[acc]);
