@@ -31,7 +31,13 @@ if str(ROOT) not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-METRIC = "query-context pairs/sec at seq_len=2048, base-130M"
+
+
+def metric_name(args) -> str:
+    """BASELINE.json's metric for the default workload; other --model/--seq-len runs name themselves."""
+    return f"query-context pairs/sec at seq_len={args.seq_len}, {args.model}"
+
+
 UNIT = "pairs/s"
 THRESHOLD = 0.1
 
@@ -159,7 +165,7 @@ def run_reference(args, world: int, rank: int) -> None:
     sample = f"{per_step} blocks of {args.seq_len} tokens per step, {args.steps} steps, HF ModernBERT fp32 sdpa on CPU"
     line = {
         "impl": "reference",
-        "metric": METRIC,
+        "metric": metric_name(args),
         "value": value,
         "unit": UNIT,
         "n_gpus": args.gpus,
@@ -192,7 +198,6 @@ def main() -> None:
         raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback)")
     from open_provence_b200 import synthetic as syn
     from open_provence_b200.engine import Engine
-    from oracle.modernbert_numpy import algorithmic_flops_per_pair
 
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -309,7 +314,7 @@ def main() -> None:
     dom_ms = prof[dom]["ms"] / max(1, prof[dom]["launches"])
     achieved_tf = gemm_flops[dom] / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-    flops_pair = algorithmic_flops_per_pair(cfg, args.seq_len) if args.mode == "dense" else None
+    flops_pair = syn.algorithmic_flops_per_pair(cfg, args.seq_len) if args.mode == "dense" else None
     step_tf = (flops_pair * args.batch / (ms_per_step * 1e-3) / 1e12) if flops_pair else None
     roofline = {
         "bound": "tensor",
@@ -344,7 +349,7 @@ def main() -> None:
         }
 
     line = {
-        "metric": METRIC,
+        "metric": metric_name(args),
         "value": round(value, 2),
         "unit": UNIT,
         "n_gpus": world,

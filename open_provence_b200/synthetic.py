@@ -136,3 +136,17 @@ def make_workload(cfg: dict[str, Any], n_pairs: int, seq_len: int, *, mode: str 
         "seq_len": seq_len,
         "mode": mode,
     }
+
+
+def algorithmic_flops_per_pair(cfg: dict[str, Any], S: int, num_labels: int = 1) -> float:
+    """SURVEY.md section 8(d) / BASELINE.md section 3: F(S) = S.L.(8H^2 + 6HI) + n_glob.4H.S^2 + n_loc.4H.P(S)
+    + 2H^2 + 2H.num_labels + 4HS, with P(S) the exact band pair count; 1 MAC = 2 FLOP, valid tokens only."""
+    H, L, I = int(cfg["hidden_size"]), int(cfg["num_hidden_layers"]), int(cfg["intermediate_size"])
+    half = int(cfg.get("local_attention", 128)) // 2
+    every = int(cfg.get("global_attn_every_n_layers", 3))
+    layer_types = cfg.get("layer_types")
+    n_glob = sum(1 for l in range(L) if (layer_types[l] == "full_attention" if layer_types else l % every == 0))
+    i = np.arange(S)
+    band = int((np.minimum(S - 1, i + half) - np.maximum(0, i - half) + 1).sum())
+    return float(S * L * (8 * H * H + 6 * H * I) + n_glob * 4 * H * S * S + (L - n_glob) * 4 * H * band
+                 + 2 * H * H + 2 * H * num_labels + S * 4 * H)

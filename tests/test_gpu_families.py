@@ -1,0 +1,68 @@
+"""Engine forward at the dimensions of the four published model families (SURVEY.md section 8 dims
+table), against the numpy oracle on the same seeded weights and ragged packed batches.
+
+The golden fixtures produced by the reference cover a tiny 128-wide model; these cases exercise the
+tile shapes the real checkpoints hit (H = 256 / 512 / 768, I = 1024 / 2048 / 3072 / 1152, 4-12 heads)
+with a reduced layer count (global, local, local, global) so the fp64 oracle finishes in seconds.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from open_provence_b200 import synthetic as syn  # noqa: E402
+from open_provence_b200.engine import Engine  # noqa: E402
+from oracle import modernbert_numpy as onp  # noqa: E402
+
+FAMILIES = ["xsmall-30M", "base-130M", "large-310M", "en-gte-149M"]
+LENGTHS = [1, 7, 64, 129, 200, 257, 385, 130]  # below / at / across the 128-token tile and 64-token band edges
+
+
+def _case(name: str, layers: int = 4, vocab: int = 1024):
+    cfg = syn.backbone_config(name)
+    cfg["num_hidden_layers"] = layers
+    cfg["vocab_size"] = vocab
+    sd = syn.random_state_dict(cfg, seed=7)
+    rng = np.random.default_rng(11)
+    seqs = [rng.integers(3, vocab, size=n).tolist() for n in LENGTHS]
+    return cfg, sd, seqs
+
+
+def _run(cfg, sd, seqs, dtype):
+    eng = Engine(cfg, sd, device="cuda", dtype=dtype, num_labels=1)
+    ids = torch.tensor([t for s in seqs for t in s], dtype=torch.int32, device="cuda")
+    cu = torch.tensor(np.concatenate([[0], np.cumsum([len(s) for s in seqs])]), dtype=torch.int32, device="cuda")
+    prune, rank = eng.forward_packed(ids, cu, max(len(s) for s in seqs))
+    torch.cuda.synchronize()
+    return prune.cpu().double().numpy(), rank.cpu().double().numpy()
+
+
+@pytest.fixture(scope="module", params=FAMILIES)
+def family(request):
+    cfg, sd, seqs = _case(request.param)
+    w64 = {k: v.double().numpy() for k, v in sd.items()}
+    ref_rank, ref_prune = onp.forward_batch(seqs, w64, cfg)
+    return request.param, cfg, sd, seqs, ref_rank, np.concatenate(ref_prune)
+
+
+def test_family_fp32_within_1e5(family):
+    name, cfg, sd, seqs, ref_rank, ref_prune = family
+    prune, rank = _run(cfg, sd, seqs, "fp32")
+    e_rank, e_prune = np.abs(rank - ref_rank).max(), np.abs(prune - ref_prune).max()
+    print(f"{name} fp32 engine vs fp64 oracle: rank {e_rank:.2e} prune {e_prune:.2e} (|prune| max {np.abs(ref_prune).max():.1f})")
+    assert e_rank < 1e-5 and e_prune < 2e-5 * max(1.0, np.abs(ref_prune).max())
+
+
+def test_family_bf16_close(family):
+    name, cfg, sd, seqs, ref_rank, ref_prune = family
+    prune, rank = _run(cfg, sd, seqs, "bf16")
+    scale = max(1.0, np.abs(ref_prune).max())
+    e_rank, e_prune = np.abs(rank - ref_rank).max(), np.abs(prune - ref_prune).max()
+    print(f"{name} bf16 engine vs fp64 oracle: rank {e_rank:.2e} prune {e_prune:.2e} (|prune| max {scale:.1f})")
+    assert np.isfinite(prune).all() and np.isfinite(rank).all()
+    # bf16 operands (2^-9 relative rounding) with fp32 accumulation / residual / LN / softmax
+    assert e_rank < 2e-2 and e_prune < 1e-2 * scale

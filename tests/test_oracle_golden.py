@@ -6,6 +6,7 @@ import numpy as np
 
 from oracle import modernbert_numpy as onp
 from oracle import postprocess_numpy as opp
+from open_provence_b200 import synthetic as syn
 
 
 def _unpadded(golden):
@@ -48,6 +49,12 @@ def test_score_conversion_matches_recorded_blocks(process_golden):
     assert abs(score - case["result"]["reranking_score"]) < 1e-7
     probs = opp.keep_probs_from_logits(np.asarray(block["prune_logits"], dtype=np.float32))
     assert probs.dtype == np.float32 and 0.0 <= probs.min() and probs.max() <= 1.0
+
+
+def test_package_flops_formula_equals_oracle():
+    for name, S in [("base-130M", 2048), ("xsmall-30M", 512), ("large-310M", 4096), ("en-gte-149M", 8192)]:
+        cfg = syn.backbone_config(name)
+        assert syn.algorithmic_flops_per_pair(cfg, S) == onp.algorithmic_flops_per_pair(cfg, S)
 
 
 def test_flops_formula_matches_baseline_table():
