@@ -54,8 +54,8 @@ def parse_args():
     ap.add_argument("--mode", default="dense", choices=["dense", "ragged"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-pairs", type=int, default=4, help="pairs in the bounded CPU-baseline sample")
-    ap.add_argument("--ref-pairs-per-step", type=int, default=2)
+    ap.add_argument("--cpu-pairs", type=int, default=32, help="pairs in the bounded CPU-baseline sample")
+    ap.add_argument("--ref-pairs-per-step", type=int, default=4)
     return ap.parse_args()
 
 
@@ -189,10 +189,15 @@ def run_reference(args, world: int, rank: int) -> None:
 
 def main() -> None:
     args = parse_args()
-    world, rank, local = dist_setup(args)
     if args.impl == "reference":
-        run_reference(args, world, rank)
+        # CPU only: no process group; under torchrun rank 0 alone runs it, with every host thread it can use
+        # (torchrun exports OMP_NUM_THREADS=1, which would otherwise pin the baseline to one core)
+        rank = int(os.environ.get("RANK", "0"))
+        if rank == 0:
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+            run_reference(args, int(os.environ.get("WORLD_SIZE", "1")), rank)
         return
+    world, rank, local = dist_setup(args)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback)")
