@@ -120,7 +120,8 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
 
 /* Process-wide tuning switches (tests, profiling).  "attention_impl": bf16 attention kernel,
  * 0 = mma.sync flash kernel (v1), 1 = tcgen05 kernel with P in TMEM (default), 2 = tcgen05 kernel with P
- * staged through shared memory. */
+ * staged through shared memory.  "attention_trace_ptr": device buffer for the clock64() timeline of
+ * tools/attn_check.py (0 = off, the product setting). */
 int opv_set_option(const char* name, int64_t value);
 
 /* Per-kernel-class timing of the forward, measured with CUDA events on the launch stream.

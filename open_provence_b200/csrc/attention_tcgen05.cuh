@@ -46,7 +46,11 @@ struct FaSmemLayout {
 template <bool P_IN_TMEM>
 __global__ void __launch_bounds__(kFaThreads, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
-                         const int32_t* __restrict__ cu_seqlens, const int H, const int half_window) {
+                         const int32_t* __restrict__ cu_seqlens, const int H, const int half_window,
+                         long long* __restrict__ trace) {
+  // trace (tools/attn_check.py only; nullptr in the product): clock64() stamps of CTA (1,0,0), 16 slots per key
+  // block: softmax warp 0 [0 s_full seen, 1 scores read, 4 pv_done seen, 5 P published], MMA warp [6 S(i) issued,
+  // 7 PV(i) issued], softmax warp w [8+2w scores read, 9+2w P published].
   using L = FaSmemLayout<P_IN_TMEM>;
   const int seq = blockIdx.z, head = blockIdx.y;
   const int begin = cu_seqlens[seq];
@@ -75,6 +79,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const bool global = half_window < 0;
+  const bool tracing = trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+#define OPV_FA_STAMP(blk, slot) do { if (tracing) trace[(blk) * 16 + (slot)] = clock64(); } while (0)
 
   // Key blocks of 128: global layers walk [0, n); local layers walk [q0 - w, q0 + 128 + w) -- the band of this
   // query tile -- starting at an UNALIGNED key (TMA zero-fills rows before the tensor, rows of the previous
@@ -105,7 +111,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for ptxas: a per-thread TMEM address makes every tcgen05.mma an ELECT / R2UR.BROADCAST waterfall loop
 
   if (warp >= 4) {
     setmaxnreg_dec<40>();
@@ -143,7 +149,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
         mbar_wait(&k_full[st], (i / kFaKvStages) & 1);
         if (i > 0) mbar_wait(s_empty, (i - 1) & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t k_addr = smem_u32(sK + st * kFaTileBytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -151,6 +157,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
                          k != 0 ? 1u : 0u);
           umma_commit(&k_empty[st]);
           umma_commit(s_full);
+          OPV_FA_STAMP(i, 6);
         }
         __syncwarp();
       };
@@ -162,7 +169,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
         mbar_wait(&v_full[st], (i / kFaKvStages) & 1);
         mbar_wait(p_full, i & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t v_addr = smem_u32(sV + st * kFaTileBytes);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {  // 16 keys per MMA: two 8-key groups of 1024 B
@@ -177,6 +184,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
           }
           umma_commit(&v_empty[st]);
           umma_commit(pv_done);
+          OPV_FA_STAMP(i, 7);
         }
         __syncwarp();
       }
@@ -204,8 +212,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
     for (int i = 0; i < nb; ++i) {
       mbar_wait(s_full, i & 1);
       tc_fence_after();
+      if (warp == 0) OPV_FA_STAMP(i, 0);
       uint32_t sr[128];
       tmem_ld_32x32b_2x64(t_s, sr);
+      if (warp == 0) OPV_FA_STAMP(i, 1);
+      OPV_FA_STAMP(i, 8 + 2 * warp);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);  // the MMA warp may overwrite S with S(i+1)
@@ -214,7 +225,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
       // row_first..row_first+31): skipped when no row may see it, unmasked when every row sees all of it.
       const int key0 = key_base + i * kFaBlockN;
       int kind[4];  // 0 = skip, 1 = full, 2 = mixed
-      float mx = -CUDART_INF_F;
+      float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;  // independent FMNMX3 chains
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         const int c_lo = key0 + 32 * ch, c_hi = c_lo + 31;
@@ -228,8 +239,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
           }
         }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(sr[32 * ch + c]));
+        for (int c = 0; c < 32; c += 8) {
+          mx0 = fmax3(mx0, __uint_as_float(sr[32 * ch + c + 0]), __uint_as_float(sr[32 * ch + c + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(sr[32 * ch + c + 2]), __uint_as_float(sr[32 * ch + c + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(sr[32 * ch + c + 4]), __uint_as_float(sr[32 * ch + c + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(sr[32 * ch + c + 6]), __uint_as_float(sr[32 * ch + c + 7]));
+        }
       }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float m_cand = fmaxf(m_run, mx * scale_log2);
       const bool upd = (m_cand - m_run) > kFaRescaleThreshold;  // false when both are -inf (NaN)
       const float m_new = upd ? m_cand : m_run;
@@ -259,6 +276,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
       if (i > 0) {
         mbar_wait(pv_done, (i - 1) & 1);  // O holds blocks < i and the P buffer is free again
         tc_fence_after();
+        if (warp == 0) OPV_FA_STAMP(i, 4);
         if (__any_sync(0xffffffffu, upd)) {
           uint32_t orr[64];
           tmem_ld_32x32b_x64(t_o, orr);
@@ -282,6 +300,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (warp == 0) OPV_FA_STAMP(i, 5);
+      OPV_FA_STAMP(i, 9 + 2 * warp);
     }
 
     // epilogue: O / l -> bf16 -> out[begin + row, head*64 : head*64+64]
@@ -304,6 +324,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
     }
   }
 
+#undef OPV_FA_STAMP
   tc_fence_before();
   __syncthreads();
   if (warp == 6) tmem_dealloc(tmem_base, kFaTmemCols);

@@ -96,6 +96,7 @@ int g_num_sms = 0;
 bool g_attrs_set = false;
 // bf16 attention kernel: 0 = mma.sync v1, 1 = tcgen05 with P in TMEM (default), 2 = tcgen05 with P in smem
 int g_attention_impl = 1;
+long long* g_attention_trace = nullptr;  // device buffer for clock64() stamps (tools/attn_check.py); nullptr in the product
 // bf16 GEMM with N % 256 == 0: 1 = CTA-pair kernel (cta_group::2, 256 x 256 tiles), 0 = single-CTA kernel
 int g_gemm_pair = 1;
 
@@ -279,10 +280,10 @@ int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, i
     dim3 grid((max_seqlen + opv::kFaBlockM - 1) / opv::kFaBlockM, heads, n_seqs);
     if (g_attention_impl == 1)
       opv::attention_tcgen05_kernel<true><<<grid, opv::kFaThreads, opv::FaSmemLayout<true>::kTotal, s>>>(
-          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window);
+          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, g_attention_trace);
     else
       opv::attention_tcgen05_kernel<false><<<grid, opv::kFaThreads, opv::FaSmemLayout<false>::kTotal, s>>>(
-          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window);
+          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, g_attention_trace);
     OPV_LAUNCH_CHECK("attention_tcgen05_kernel");
   } else if (dtype == OPV_DTYPE_BF16) {
     dim3 grid((max_seqlen + opv::kAttBlockM - 1) / opv::kAttBlockM, heads, n_seqs);
@@ -770,6 +771,10 @@ int opv_set_option(const char* name, int64_t value) {
   if (strcmp(name, "attention_impl") == 0) {
     if (value < 0 || value > 2) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_impl must be 0, 1 or 2");
     g_attention_impl = static_cast<int>(value);
+    return OPV_OK;
+  }
+  if (strcmp(name, "attention_trace_ptr") == 0) {
+    g_attention_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));
     return OPV_OK;
   }
   if (strcmp(name, "gemm_pair") == 0) {

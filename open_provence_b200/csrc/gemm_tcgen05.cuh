@@ -249,7 +249,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for ptxas: a per-thread TMEM address makes every tcgen05.mma an ELECT / R2UR.BROADCAST waterfall loop
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -259,7 +259,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], L::kStageA + L::kStageB);
           tma_load_2d(smem_a + stage * L::kStageA, &tm_a, &full_bar[stage], kb * kGemmBlockK, m_blk * kGemmBlockM);
           tma_load_2d(smem_b + stage * L::kStageB, &tm_b, &full_bar[stage], kb * kGemmBlockK, n_blk * BLOCK_N);
@@ -282,7 +282,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_base = smem_u32(smem_a + stage * L::kStageA);
           const uint32_t b_base = smem_u32(smem_b + stage * L::kStageB);
 #pragma unroll
@@ -416,7 +416,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
   tc_fence_before();
   cluster_sync_all();  // barrier inits of both CTAs visible before any remote arrive / multicast commit
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for ptxas: a per-thread TMEM address makes every tcgen05.mma an ELECT / R2UR.BROADCAST waterfall loop
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------
@@ -428,7 +428,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
       const int wrow0 = n_blk * BLOCK_N + cta_rank * 128;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (lane == 0) {
+        if (elect_one()) {
           if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (L::kStageA + L::kStageB));
           tma_load_2d_pair(smem_a + stage * L::kStageA, &tm_a, &full_bar[stage], kb * kGemmBlockK, row0);
           tma_load_2d_pair(smem_b + stage * L::kStageB, &tm_b, &full_bar[stage], kb * kGemmBlockK, wrow0);
@@ -452,7 +452,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);  // both CTAs' TMA bytes have landed
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t a_base = smem_u32(smem_a + stage * L::kStageA);
             const uint32_t b_base = smem_u32(smem_b + stage * L::kStageB);
 #pragma unroll

@@ -2,7 +2,7 @@
 """Correctness + timing of one bf16 attention kernel (run once per impl, each in its own process so that a
 device trap in one variant cannot poison the others).
 
-    python tools/attn_check.py <impl 0|1|2> [half_window]
+    python tools/attn_check.py <impl 0|1|2> [half_window] [trace]
 """
 import sys
 from pathlib import Path
@@ -68,3 +68,16 @@ else:
     pairs = sum(min(S - 1, i + hw) - max(0, i - hw) + 1 for i in range(S))
     flops = 4.0 * heads * 64 * pairs * B
 print(f"impl={impl} hw={hw} B={B} S={S} heads={heads}: {ms:.3f} ms/launch, {flops / ms / 1e9:.1f} TFLOP/s (algorithmic)", flush=True)
+
+if len(sys.argv) > 3 and sys.argv[3] == "trace":
+    nb = (S + 127) // 128 if hw < 0 else 2
+    buf = torch.zeros(16 * 64, dtype=torch.int64, device=dev)
+    ops.set_option("attention_trace_ptr", buf.data_ptr())
+    ops.attention(qkv, cu, S, heads, hw)
+    torch.cuda.synchronize()
+    ops.set_option("attention_trace_ptr", 0)
+    t = buf.cpu().numpy().reshape(64, 16)[:nb]
+    t0 = t[0, 0]
+    print("block: s_full  S_loaded  max_done  exp_done  pv_done  P_stored | S_issued(i) PV_issued(i) | per softmax warp: S_loaded, P_stored x4   (cycles since block 0 s_full)")
+    for i in range(nb):
+        print(f"{i:3d}: " + " ".join(f"{int(v - t0):8d}" if v else "       -" for v in t[i]))

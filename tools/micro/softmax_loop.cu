@@ -1,0 +1,58 @@
+// The attention softmax inner loop in isolation (no MMA / TMEM / barriers): per "block" each thread does
+// 64 FMNMX3 + 128 x (FFMA, MUFU.EX2, FADD) + 64 F2FP over 128 register-resident scores.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o softmax_loop softmax_loop.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fmax3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ unsigned pack(float lo, float hi) { unsigned r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+
+template <int VARIANT>  // 0 = full, 1 = no MUFU (FMUL instead), 2 = no max, 3 = no pack
+__global__ void __launch_bounds__(256, 1) k(const float* in, unsigned* out, long long* clk, int iters) {
+  float sr[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) sr[i] = in[i * 256 + threadIdx.x];
+  float m = 0.f, l = 0.f;
+  unsigned acc = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    float mx0 = -1e30f, mx1 = -1e30f, mx2 = -1e30f, mx3 = -1e30f;
+    if (VARIANT != 2) {
+#pragma unroll
+      for (int c = 0; c < 128; c += 8) {
+        mx0 = fmax3(mx0, sr[c], sr[c + 1]); mx1 = fmax3(mx1, sr[c + 2], sr[c + 3]);
+        mx2 = fmax3(mx2, sr[c + 4], sr[c + 5]); mx3 = fmax3(mx3, sr[c + 6], sr[c + 7]);
+      }
+    }
+    m = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * 0.18f + l * 1e-30f;
+    float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+    for (int c = 0; c < 128; c += 4) {
+      const float xa = fmaf(sr[c], 0.18f, -m), xb = fmaf(sr[c + 1], 0.18f, -m), xc = fmaf(sr[c + 2], 0.18f, -m), xd = fmaf(sr[c + 3], 0.18f, -m);
+      float a, b, e, f;
+      if (VARIANT == 1) { a = xa * 0.5f, b = xb * 0.5f, e = xc * 0.5f, f = xd * 0.5f; }
+      else { a = ex2(xa), b = ex2(xb), e = ex2(xc), f = ex2(xd); }
+      s0 += a, s1 += b, s2 += e, s3 += f;
+      if (VARIANT != 3) acc ^= pack(a, b) + pack(e, f);
+    }
+    l = l * 0.5f + (s0 + s1) + (s2 + s3);
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc + __float_as_uint(l);
+  if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
+}
+
+template <int V>
+void run(const char* name) {
+  int sms = 148, iters = 2000;
+  float* in; unsigned* out; long long* clk;
+  cudaMalloc(&in, 32768 * 4); cudaMemset(in, 0, 32768 * 4);
+  cudaMalloc(&out, sms * 256 * 4); cudaMalloc(&clk, sms * 8);
+  k<V><<<sms, 256>>>(in, out, clk, iters); k<V><<<sms, 256>>>(in, out, clk, iters);
+  cudaDeviceSynchronize();
+  long long h[148]; cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < sms; ++i) avg += h[i]; avg /= sms;
+  printf("%-28s %7.0f clk per 128-score block (2 warps per scheduler)  %s\n", name, avg / iters, cudaGetErrorString(cudaGetLastError()));
+}
+int main() { run<0>("full"); run<1>("no MUFU (FMUL)"); run<2>("no max"); run<3>("no pack"); return 0; }
