@@ -225,53 +225,90 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
       // row_first..row_first+31): skipped when no row may see it, unmasked when every row sees all of it.
       const int key0 = key_base + i * kFaBlockN;
       int kind[4];  // 0 = skip, 1 = full, 2 = mixed
-      float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;  // independent FMNMX3 chains
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         const int c_lo = key0 + 32 * ch, c_hi = c_lo + 31;
         kind[ch] = (c_hi < any_lo || c_lo > any_hi) ? 0 : ((c_lo >= all_lo && c_hi <= all_hi) ? 1 : 2);
-        if (kind[ch] == 0) continue;
-        if (kind[ch] == 2) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const bool ok = static_cast<uint32_t>(c_lo + c - k_lo) <= k_span;
-            if (!ok) sr[32 * ch + c] = 0xff800000u;  // -inf
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          mx0 = fmax3(mx0, __uint_as_float(sr[32 * ch + c + 0]), __uint_as_float(sr[32 * ch + c + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(sr[32 * ch + c + 2]), __uint_as_float(sr[32 * ch + c + 3]));
-          mx2 = fmax3(mx2, __uint_as_float(sr[32 * ch + c + 4]), __uint_as_float(sr[32 * ch + c + 5]));
-          mx3 = fmax3(mx3, __uint_as_float(sr[32 * ch + c + 6]), __uint_as_float(sr[32 * ch + c + 7]));
-        }
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      const float m_cand = fmaxf(m_run, mx * scale_log2);
-      const bool upd = (m_cand - m_run) > kFaRescaleThreshold;  // false when both are -inf (NaN)
-      const float m_new = upd ? m_cand : m_run;
-      const float corr = upd ? ex2_approx(m_run - m_new) : 1.0f;
-      const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-      m_run = m_new;
-
+      // Every block of a global layer except a sequence's last one is fully visible to every row.  That case
+      // runs as ONE straight-line basic block (no per-chunk branches) so that ptxas can keep MUFU.EX2 results in
+      // flight across the whole row: the softmax loop alone needs ~1200 cycles per block for a single warp
+      // (tools/micro/softmax_loop.cu), the branchy general path below measured ~2500 inside this kernel.
+      const bool all_full = (kind[0] & kind[1] & kind[2] & kind[3]) == 1 && (kind[0] | kind[1] | kind[2] | kind[3]) == 1;
       uint32_t pr[64];
-      float sum0 = 0.f, sum1 = 0.f;
+      float corr;
+      bool upd;
+      if (all_full) {
+        float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        if (kind[ch] == 0) {
+        for (int c = 0; c < 128; c += 8) {
+          mx0 = fmax3(mx0, __uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7]));
+        }
+        const float m_cand = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);  // finite
+        upd = (m_cand - m_run) > kFaRescaleThreshold;
+        const float m_new = upd ? m_cand : m_run;
+        corr = upd ? ex2_approx(m_run - m_new) : 1.0f;
+        m_run = m_new;
+        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) pr[16 * ch + c] = 0u;
-        } else {
+        for (int c = 0; c < 64; c += 2) {
+          const float a = ex2_approx(fmaf(__uint_as_float(sr[2 * c]), scale_log2, -m_new));
+          const float b = ex2_approx(fmaf(__uint_as_float(sr[2 * c + 1]), scale_log2, -m_new));
+          const float e = ex2_approx(fmaf(__uint_as_float(sr[2 * c + 2]), scale_log2, -m_new));
+          const float f = ex2_approx(fmaf(__uint_as_float(sr[2 * c + 3]), scale_log2, -m_new));
+          sum0 += a, sum1 += b, sum2 += e, sum3 += f;
+          pr[c] = pack_bf16x2(a, b);
+          pr[c + 1] = pack_bf16x2(e, f);
+        }
+        l_run = l_run * corr + ((sum0 + sum1) + (sum2 + sum3));
+      } else {
+        float mx = -CUDART_INF_F;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float a = ex2_approx(fmaf(__uint_as_float(sr[32 * ch + 2 * c]), scale_log2, -m_use));
-            const float b = ex2_approx(fmaf(__uint_as_float(sr[32 * ch + 2 * c + 1]), scale_log2, -m_use));
-            sum0 += a, sum1 += b;
-            pr[16 * ch + c] = pack_bf16x2(a, b);
+        for (int ch = 0; ch < 4; ++ch) {
+          if (kind[ch] == 0) continue;
+          if (kind[ch] == 2) {
+            const int c_lo = key0 + 32 * ch;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const bool ok = static_cast<uint32_t>(c_lo + c - k_lo) <= k_span;
+              if (!ok) sr[32 * ch + c] = 0xff800000u;  // -inf
+            }
+          }
+          float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            mx0 = fmax3(mx0, __uint_as_float(sr[32 * ch + c + 0]), __uint_as_float(sr[32 * ch + c + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(sr[32 * ch + c + 2]), __uint_as_float(sr[32 * ch + c + 3]));
+          }
+          mx = fmax3(mx, mx0, mx1);
+        }
+        const float m_cand = fmaxf(m_run, mx * scale_log2);
+        upd = (m_cand - m_run) > kFaRescaleThreshold;  // false when both are -inf (NaN)
+        const float m_new = upd ? m_cand : m_run;
+        corr = upd ? ex2_approx(m_run - m_new) : 1.0f;
+        const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
+        m_run = m_new;
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          if (kind[ch] == 0) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pr[16 * ch + c] = 0u;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const float a = ex2_approx(fmaf(__uint_as_float(sr[32 * ch + 2 * c]), scale_log2, -m_use));
+              const float b = ex2_approx(fmaf(__uint_as_float(sr[32 * ch + 2 * c + 1]), scale_log2, -m_use));
+              sum0 += a, sum1 += b;
+              pr[16 * ch + c] = pack_bf16x2(a, b);
+            }
           }
         }
+        l_run = l_run * corr + (sum0 + sum1);
       }
-      l_run = l_run * corr + (sum0 + sum1);
 
       if (i > 0) {
         mbar_wait(pv_done, (i - 1) & 1);  // O holds blocks < i and the P buffer is free again

@@ -44,15 +44,15 @@ __global__ void __launch_bounds__(256, 1) k(const float* in, unsigned* out, long
 }
 
 template <int V>
-void run(const char* name) {
+void run(const char* name, int threads = 256) {
   int sms = 148, iters = 2000;
   float* in; unsigned* out; long long* clk;
   cudaMalloc(&in, 32768 * 4); cudaMemset(in, 0, 32768 * 4);
   cudaMalloc(&out, sms * 256 * 4); cudaMalloc(&clk, sms * 8);
-  k<V><<<sms, 256>>>(in, out, clk, iters); k<V><<<sms, 256>>>(in, out, clk, iters);
+  k<V><<<sms, threads>>>(in, out, clk, iters); k<V><<<sms, threads>>>(in, out, clk, iters);
   cudaDeviceSynchronize();
   long long h[148]; cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
   double avg = 0; for (int i = 0; i < sms; ++i) avg += h[i]; avg /= sms;
-  printf("%-28s %7.0f clk per 128-score block (2 warps per scheduler)  %s\n", name, avg / iters, cudaGetErrorString(cudaGetLastError()));
+  printf("%-28s threads=%d %7.0f clk per 128-score block  %s\n", name, threads, avg / iters, cudaGetErrorString(cudaGetLastError()));
 }
-int main() { run<0>("full"); run<1>("no MUFU (FMUL)"); run<2>("no max"); run<3>("no pack"); return 0; }
+int main() { run<0>("full", 128); run<1>("no MUFU (FMUL)", 128); run<0>("full"); run<1>("no MUFU (FMUL)"); run<2>("no max"); run<3>("no pack"); return 0; }
