@@ -37,6 +37,7 @@ from .host_text import (
     resolve_sentence_splitter,
     split_token_lists,
     tokenize_batch,
+    decode_batch,
 )
 from .scoring import BlockTable, DeviceScorer
 
@@ -658,8 +659,7 @@ class OpenProvenceModel:
         timing["fragment_split_seconds"] += perf_counter() - t0
         t0 = perf_counter()
         all_frags = [f for p in plans for f in p.fragments]
-        texts = self.tokenizer.batch_decode([f.token_ids for f in all_frags], skip_special_tokens=True,
-                                            clean_up_tokenization_spaces=False) if all_frags else []
+        texts = decode_batch(self.tokenizer, [f.token_ids for f in all_frags])
         at = 0
         for p in plans:
             n = len(p.fragments)

@@ -80,6 +80,7 @@ class DeviceScorer:
 
     def run(self, table: BlockTable, threshold: float) -> dict[str, np.ndarray]:
         """Single-GPU path: score every block, then prune."""
+        self.last_n_blocks = table.n_blocks
         rank_score, frag_mean_dev, kept = self.score_blocks(table, np.arange(table.n_blocks))
         return self.prune(table, rank_score, frag_mean_dev, kept, threshold)
 
