@@ -347,10 +347,10 @@ struct LaunchScope {
 };
 
 struct WorkspaceLayout {
-  size_t h, x, qkv, attn, act, u, pos, total;
+  size_t h, x, qkv, attn, act, u, pos, cls, y, total;
 };
 
-static WorkspaceLayout workspace_layout(const opv_engine* e, int64_t T) {
+static WorkspaceLayout workspace_layout(const opv_engine* e, int64_t T, int64_t n_seqs) {
   const size_t H = e->cfg.hidden_size, I = e->cfg.intermediate_size, elt = e->elt;
   const bool unfused = e->cfg.dtype == OPV_DTYPE_F32 || !e->cfg.fuse_epilogues;
   WorkspaceLayout l;
@@ -368,6 +368,9 @@ static WorkspaceLayout workspace_layout(const opv_engine* e, int64_t T) {
   l.act = take(rows * I * elt);
   l.u = take(unfused ? rows * 2 * I * elt : 0);
   l.pos = take(rows * 4);
+  const size_t seqs = static_cast<size_t>(n_seqs > 0 ? n_seqs : 1);
+  l.cls = take(seqs * H * 4);  // rank head: LN(CLS row)
+  l.y = take(seqs * H * 4);    // rank head: gelu(dense(cls))
   l.total = off;
   return l;
 }
@@ -451,9 +454,8 @@ int opv_destroy(opv_handle h) {
 }
 
 size_t opv_workspace_bytes(opv_handle h, int64_t max_tokens, int32_t max_seqs) {
-  (void)max_seqs;
   if (!h) return 0;
-  return workspace_layout(h, max_tokens).total + 1024;
+  return workspace_layout(h, max_tokens, max_seqs).total + 1024;
 }
 
 int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_seqlens, int32_t n_seqs,
@@ -472,7 +474,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
   const opv_config& c = e->cfg;
   const int H = c.hidden_size, I = c.intermediate_size, L = c.num_layers, heads = c.num_heads;
   const int64_t T = n_tokens;
-  const WorkspaceLayout wl = workspace_layout(e, T);
+  const WorkspaceLayout wl = workspace_layout(e, T, n_seqs);
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d_workspace) + 1023) & ~uintptr_t(1023));
   if (static_cast<size_t>(ws - static_cast<uint8_t*>(d_workspace)) + wl.total > workspace_bytes)
     return fail(OPV_ERR_WORKSPACE, "workspace too small: need %zu bytes, have %zu", wl.total + 1024, workspace_bytes);
@@ -636,14 +638,24 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
   }
 
   {
-    LaunchScope sc(e, stream, OPV_PROF_HEADS, 2);
+    LaunchScope sc(e, stream, OPV_PROF_HEADS, 4);
     rc = launch_final_prune(h, e->w.d_final_norm, e->w.d_prune_weight, e->w.d_prune_bias, d_prune_logits, T, H,
                             c.norm_eps, stream);
     if (rc) return rc;
-    opv::rank_head_kernel<<<n_seqs, 256, (2 * H + 8) * sizeof(float), stream>>>(
-        h, d_cu_seqlens, e->w.d_final_norm, e->w.d_head_dense, e->w.d_head_norm, e->w.d_cls_weight, e->w.d_cls_bias,
-        d_rank_logits, H, c.num_labels, c.norm_eps);
-    OPV_LAUNCH_CHECK("rank_head_kernel");
+    float* cls = reinterpret_cast<float*>(ws + wl.cls);
+    float* y = reinterpret_cast<float*>(ws + wl.y);
+    opv::rank_head_cls_ln_kernel<<<n_seqs, 32, 0, stream>>>(h, d_cu_seqlens, e->w.d_final_norm, cls, H, c.norm_eps);
+    OPV_LAUNCH_CHECK("rank_head_cls_ln_kernel");
+    {
+      dim3 grid(H / opv::kRankFeatTile, (n_seqs + opv::kRankSeqTile - 1) / opv::kRankSeqTile);
+      const size_t smem = static_cast<size_t>(opv::kRankSeqTile) * H * sizeof(float);
+      OPV_DISPATCH_VEC(H, opv::rank_head_dense_kernel<VEC>
+                           <<<grid, opv::kRankFeatTile * 32, smem, stream>>>(cls, e->w.d_head_dense, y, n_seqs));
+      OPV_LAUNCH_CHECK("rank_head_dense_kernel");
+    }
+    opv::rank_head_out_kernel<<<n_seqs, 32, 0, stream>>>(y, e->w.d_head_norm, e->w.d_cls_weight, e->w.d_cls_bias,
+                                                        d_rank_logits, H, c.num_labels, c.norm_eps);
+    OPV_LAUNCH_CHECK("rank_head_out_kernel");
   }
   return OPV_OK;
 }

@@ -143,71 +143,82 @@ final_ln_prune_kernel(const float* __restrict__ h, const float* __restrict__ w, 
   }
 }
 
-// K13: rank_logits[s] = classifier(LN(gelu(dense(LN(h[cls_s]; final_norm))); head.norm)) (HF:621-634,493-502)
-// One CTA per sequence; "cls" pooling only.
-__device__ __forceinline__ float block_sum_256(float v, float* red) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float t = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) t += red[i];
-  return t;
-}
-__global__ void __launch_bounds__(256)
-rank_head_kernel(const float* __restrict__ h, const int32_t* __restrict__ cu_seqlens,
-                 const float* __restrict__ final_norm, const float* __restrict__ dense,
-                 const float* __restrict__ head_norm, const float* __restrict__ cls_w,
-                 const float* __restrict__ cls_b, float* __restrict__ rank_logits, const int H, const int num_labels,
-                 const float eps) {
-  extern __shared__ float sm[];
-  float* cls = sm;        // [H]
-  float* y = sm + H;      // [H]
-  float* red = sm + 2 * H;  // [8]
-  const int s = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// K13: rank_logits[s] = classifier(LN(gelu(dense(LN(h[cls_s]; final_norm))); head.norm)) (HF:621-634,493-502),
+// "cls" pooling only.  Three small launches: the first version ran everything in one CTA per sequence and spent
+// 337 us per step re-reading the [H, H] dense matrix once per sequence with one dependent load at a time.
+//   stage 1 (one warp per sequence)      cls[s]  = LN(h[first token of s]; final_norm)
+//   stage 2 (8 features x 8 sequences)   y[s][j] = gelu(cls[s] . dense[j])   dense row held in registers,
+//                                                                            the 8 cls rows shared through smem
+//   stage 3 (one warp per sequence)      rank[s] = LN(y[s]; head.norm) . classifier^T + bias
+constexpr int kRankSeqTile = 8;  // 8 x H x 4 B <= 32 KB of shared memory for H <= 1024
+constexpr int kRankFeatTile = 8;  // = warps per CTA of stage 2
+
+__global__ void __launch_bounds__(32)
+rank_head_cls_ln_kernel(const float* __restrict__ h, const int32_t* __restrict__ cu_seqlens,
+                        const float* __restrict__ final_norm, float* __restrict__ cls, const int H, const float eps) {
+  const int s = blockIdx.x, lane = threadIdx.x;
   const float* row = h + static_cast<int64_t>(cu_seqlens[s]) * H;
   const float inv_h = 1.0f / static_cast<float>(H);
-
   float part = 0.f;
-  for (int i = tid; i < H; i += 256) part += row[i];
-  const float mean = block_sum_256(part, red) * inv_h;
+  for (int i = lane; i < H; i += 32) part += row[i];
+  const float mean = warp_sum(part) * inv_h;
   part = 0.f;
-  for (int i = tid; i < H; i += 256) {
+  for (int i = lane; i < H; i += 32) {
     const float d = row[i] - mean;
     part += d * d;
   }
-  const float rstd = 1.0f / sqrtf(block_sum_256(part, red) * inv_h + eps);
-  for (int i = tid; i < H; i += 256) cls[i] = (row[i] - mean) * rstd * final_norm[i];
-  __syncthreads();
+  const float rstd = 1.0f / sqrtf(warp_sum(part) * inv_h + eps);
+  for (int i = lane; i < H; i += 32) cls[static_cast<int64_t>(s) * H + i] = (row[i] - mean) * rstd * final_norm[i];
+}
 
-  for (int j = warp; j < H; j += 8) {  // dense has no bias (classifier_bias = False)
-    const float* wr = dense + static_cast<int64_t>(j) * H;
+template <int VEC>  // H = VEC * 128
+__global__ void __launch_bounds__(kRankFeatTile * 32)
+rank_head_dense_kernel(const float* __restrict__ cls, const float* __restrict__ dense, float* __restrict__ y,
+                       const int n_seqs) {
+  constexpr int H = VEC * 128;
+  extern __shared__ float sm_cls[];  // [kRankSeqTile][H]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s0 = blockIdx.y * kRankSeqTile;
+  const int ns = min(kRankSeqTile, n_seqs - s0);
+  for (int i = threadIdx.x; i < ns * (H / 4); i += blockDim.x)
+    reinterpret_cast<float4*>(sm_cls)[i] = reinterpret_cast<const float4*>(cls + static_cast<int64_t>(s0) * H)[i];
+  const int j = blockIdx.x * kRankFeatTile + warp;  // dense has no bias (classifier_bias = False)
+  float4 w[VEC];
+  load_row_f32<VEC>(dense + static_cast<int64_t>(j) * H, lane, w);
+  __syncthreads();
+  for (int s = 0; s < ns; ++s) {
+    const float* c = sm_cls + s * H;
     float acc = 0.f;
-    for (int i = lane; i < H; i += 32) acc = fmaf(cls[i], wr[i], acc);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(c + (i * 32 + lane) * 4);
+      acc += (v.x * w[i].x + v.y * w[i].y) + (v.z * w[i].z + v.w * w[i].w);
+    }
     acc = warp_sum(acc);
-    if (lane == 0) y[j] = gelu_erf(acc);
+    if (lane == 0) y[static_cast<int64_t>(s0 + s) * H + j] = gelu_erf(acc);
   }
-  __syncthreads();
+}
 
+__global__ void __launch_bounds__(32)
+rank_head_out_kernel(const float* __restrict__ y, const float* __restrict__ head_norm, const float* __restrict__ cls_w,
+                     const float* __restrict__ cls_b, float* __restrict__ rank_logits, const int H,
+                     const int num_labels, const float eps) {
+  const int s = blockIdx.x, lane = threadIdx.x;
+  const float* row = y + static_cast<int64_t>(s) * H;
+  const float inv_h = 1.0f / static_cast<float>(H);
+  float part = 0.f;
+  for (int i = lane; i < H; i += 32) part += row[i];
+  const float mean = warp_sum(part) * inv_h;
   part = 0.f;
-  for (int i = tid; i < H; i += 256) part += y[i];
-  const float mean2 = block_sum_256(part, red) * inv_h;
-  part = 0.f;
-  for (int i = tid; i < H; i += 256) {
-    const float d = y[i] - mean2;
+  for (int i = lane; i < H; i += 32) {
+    const float d = row[i] - mean;
     part += d * d;
   }
-  const float rstd2 = 1.0f / sqrtf(block_sum_256(part, red) * inv_h + eps);
-  __syncthreads();
-  for (int i = tid; i < H; i += 256) y[i] = (y[i] - mean2) * rstd2 * head_norm[i];
-  __syncthreads();
-
-  for (int l = warp; l < num_labels; l += 8) {
+  const float rstd = 1.0f / sqrtf(warp_sum(part) * inv_h + eps);
+  for (int l = 0; l < num_labels; ++l) {
     const float* wr = cls_w + static_cast<int64_t>(l) * H;
     float acc = 0.f;
-    for (int i = lane; i < H; i += 32) acc = fmaf(y[i], wr[i], acc);
+    for (int i = lane; i < H; i += 32) acc = fmaf((row[i] - mean) * rstd * head_norm[i], wr[i], acc);
     acc = warp_sum(acc);
     if (lane == 0) rank_logits[static_cast<int64_t>(s) * num_labels + l] = acc + cls_b[l];
   }
