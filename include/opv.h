@@ -153,6 +153,10 @@ int opv_fragment_means(const float* d_prune_logits, int64_t n_tokens, const int3
                        int32_t n_frags, float* d_frag_mean, const float* d_rank_logits, int32_t n_seqs,
                        int32_t num_labels, float* d_rank_score, void* stream);
 
+/* Token-level keep probabilities for the encoder.py APIs (encoder.py:429-430, 769-771):
+ *   d_keep_prob[t] = softmax(d_prune_logits[t])[1], fp32 [T]. */
+int opv_token_keep_probs(const float* d_prune_logits, int64_t n_tokens, float* d_keep_prob, void* stream);
+
 /* Per-sentence prune (standalone:3094-3134 without the string work).
  *   sentence s owns fragment means d_frag_mean[d_sent_frag_index[k]] for k in
  *   [d_sent_offsets[s], d_sent_offsets[s+1]); prob = mean (fp64) clamped to [0,1], 0.0 when it has none;

@@ -5,8 +5,25 @@ Only what the hot path needs lives here:
   _native.py   ctypes binding of libopv_sm100.so (no fallback)
   engine.py    weight packing + launches
   modeling.py  drop-in ``OpenProvenceModel`` (from_pretrained / forward / process)
+  encoder.py   drop-in ``OpenProvenceEncoder`` inference APIs (token-level pruning, chunk votes)
 """
 
 __version__ = "0.1.0"
 
-__all__ = ["__version__"]
+__all__ = ["__version__", "OpenProvenceModel", "OpenProvenceEncoder", "OpenProvenceConfig"]
+
+
+def __getattr__(name):  # lazy: importing the package must not pull torch / the shared library in
+    if name == "OpenProvenceModel":
+        from .modeling import OpenProvenceModel
+
+        return OpenProvenceModel
+    if name == "OpenProvenceEncoder":
+        from .encoder import OpenProvenceEncoder
+
+        return OpenProvenceEncoder
+    if name == "OpenProvenceConfig":
+        from .config import OpenProvenceConfig
+
+        return OpenProvenceConfig
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -95,6 +95,7 @@ SIGNATURES = {
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
          C.c_void_p],
     ),
+    "opv_token_keep_probs": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "opv_sentence_prune": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,

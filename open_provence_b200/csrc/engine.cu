@@ -702,6 +702,16 @@ int opv_fragment_means(const float* d_prune_logits, int64_t n_tokens, const int3
   return OPV_OK;
 }
 
+int opv_token_keep_probs(const float* d_prune_logits, int64_t n_tokens, float* d_keep_prob, void* stream_) {
+  if (n_tokens <= 0) return OPV_OK;
+  if (!d_prune_logits || !d_keep_prob) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_token_keep_probs: null buffer");
+  const int64_t blocks = (n_tokens + 255) / 256;
+  opv::token_keep_prob_kernel<<<static_cast<unsigned>(blocks < 4736 ? blocks : 4736), 256, 0,
+                                static_cast<cudaStream_t>(stream_)>>>(d_prune_logits, n_tokens, d_keep_prob);
+  OPV_LAUNCH_CHECK("token_keep_prob_kernel");
+  return OPV_OK;
+}
+
 int opv_sentence_prune(const float* d_frag_mean, const int32_t* d_sent_offsets, const int32_t* d_sent_frag_index,
                        int32_t n_sents, double threshold, double guard, double* d_sent_prob, uint8_t* d_keep,
                        uint8_t* d_near, void* stream_) {

@@ -280,6 +280,16 @@ __device__ __forceinline__ float keep_prob(float l0, float l1) {
   return e1 / (e0 + e1);
 }
 
+// token-level keep probabilities (encoder.py:429-430): p[t] = softmax(prune_logits[t])[1]
+__global__ void token_keep_prob_kernel(const float* __restrict__ logits, const int64_t n_tokens, float* __restrict__ prob) {
+  const float2* l2 = reinterpret_cast<const float2*>(logits);
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < n_tokens;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float2 l = __ldg(l2 + t);
+    prob[t] = keep_prob(l.x, l.y);
+  }
+}
+
 // one warp per fragment: coalesced read of the fragment's [start, end) logits, warp-shuffle sum
 __global__ void __launch_bounds__(kRowWarps * 32)
 fragment_mean_kernel(const float* __restrict__ logits, const int64_t n_tokens, const int32_t* __restrict__ ranges,

@@ -282,6 +282,15 @@ class Engine:
         N.check(rc, "opv_fragment_means")
         return frag_mean, score
 
+    def token_keep_probs(self, prune_logits: torch.Tensor) -> torch.Tensor:
+        """softmax(prune_logits)[:, 1] per packed token (device, async) -- encoder.py:429-430."""
+        n = int(prune_logits.shape[0])
+        prob = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.opv_token_keep_probs(prune_logits.data_ptr(), n, prob.data_ptr(), self._stream())
+        N.check(rc, "opv_token_keep_probs")
+        return prob
+
     def sentence_prune(
         self,
         frag_mean: torch.Tensor,
