@@ -321,14 +321,20 @@ def main() -> None:
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
     flops_pair = syn.algorithmic_flops_per_pair(cfg, args.seq_len) if args.mode == "dense" else None
     step_tf = (flops_pair * args.batch / (ms_per_step * 1e-3) / 1e12) if flops_pair else None
+    traffic = None
+    traffic_file = ROOT / "profiles" / "roofline_traffic.json"
+    if traffic_file.exists() and args.model == "base-130M" and args.seq_len == 2048 and args.batch == 64 and args.mode == "dense":
+        traffic = json.loads(traffic_file.read_text())  # one ncu --set full capture of this kernel at this shape
     roofline = {
         "bound": "tensor",
-        "kernel": "gemm_bf16_tcgen05_kernel<256, GEGLU> (mlp.Wi + GeGLU)",
+        "kernel": "gemm_bf16_tcgen05_pair_kernel<GEGLU> (mlp.Wi + GeGLU, 38 % of the step's algorithmic FLOPs)",
         "achieved": round(achieved_tf, 2),
         "peak": peak_tf,
         "unit": "TFLOP/s",
         "frac": round(achieved_tf / peak_tf, 4),
-        "traffic": None,
+        "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+        "traffic_source": traffic["source"] if traffic else None,
+        "algorithmic_bytes_per_launch": T * (2 * H + 2 * I) + 2 * 2 * I * H,
         "peak_kind": f"bf16 sustained, {peaks['source']} (MEASURED_PEAKS.json)",
         "flops_per_launch": gemm_flops[dom],
         "ms_per_launch": round(dom_ms, 4),
