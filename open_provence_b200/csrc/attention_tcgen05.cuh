@@ -50,7 +50,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
                          long long* __restrict__ trace) {
   // trace (tools/attn_check.py only; nullptr in the product): clock64() stamps of CTA (1,0,0), 16 slots per key
   // block: softmax warp 0 [0 s_full seen, 1 scores read, 4 pv_done seen, 5 P published], MMA warp [6 S(i) issued,
-  // 7 PV(i) issued], softmax warp w [8+2w scores read, 9+2w P published].
+  // 7 PV(i) issued], softmax warp w < 3 [8+2w scores read, 9+2w P published]; block 0 slots 14 / 15 = kernel entry / exit.
   using L = FaSmemLayout<P_IN_TMEM>;
   const int seq = blockIdx.z, head = blockIdx.y;
   const int begin = cu_seqlens[seq];
@@ -81,6 +81,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
   const bool global = half_window < 0;
   const bool tracing = trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
 #define OPV_FA_STAMP(blk, slot) do { if (tracing) trace[(blk) * 16 + (slot)] = clock64(); } while (0)
+  if (warp == 0) OPV_FA_STAMP(0, 14);  // kernel entry
 
   // Key blocks of 128: global layers walk [0, n); local layers walk [q0 - w, q0 + 128 + w) -- the band of this
   // query tile -- starting at an UNALIGNED key (TMA zero-fills rows before the tensor, rows of the previous
@@ -216,7 +217,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
       uint32_t sr[128];
       tmem_ld_32x32b_2x64(t_s, sr);
       if (warp == 0) OPV_FA_STAMP(i, 1);
-      OPV_FA_STAMP(i, 8 + 2 * warp);
+      if (warp < 3) OPV_FA_STAMP(i, 8 + 2 * warp);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);  // the MMA warp may overwrite S with S(i+1)
@@ -338,7 +339,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
       if (warp == 0) OPV_FA_STAMP(i, 5);
-      OPV_FA_STAMP(i, 9 + 2 * warp);
+      if (warp < 3) OPV_FA_STAMP(i, 9 + 2 * warp);
     }
 
     // epilogue: O / l -> bf16 -> out[begin + row, head*64 : head*64+64]
@@ -361,9 +362,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
     }
   }
 
-#undef OPV_FA_STAMP
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) OPV_FA_STAMP(0, 15);  // all roles done (before the TMEM release)
+#undef OPV_FA_STAMP
   if (warp == 6) tmem_dealloc(tmem_base, kFaTmemCols);
 }
 

@@ -78,6 +78,7 @@ if len(sys.argv) > 3 and sys.argv[3] == "trace":
     ops.set_option("attention_trace_ptr", 0)
     t = buf.cpu().numpy().reshape(64, 16)[:nb]
     t0 = t[0, 0]
-    print("block: s_full  S_loaded  max_done  exp_done  pv_done  P_stored | S_issued(i) PV_issued(i) | per softmax warp: S_loaded, P_stored x4   (cycles since block 0 s_full)")
+    print("block: s_full  S_loaded  max_done  exp_done  pv_done  P_stored | S_issued(i) PV_issued(i) | per softmax warp 0..2: S_loaded, P_stored   (cycles since block 0 s_full)")
     for i in range(nb):
-        print(f"{i:3d}: " + " ".join(f"{int(v - t0):8d}" if v else "       -" for v in t[i]))
+        print(f"{i:3d}: " + " ".join(f"{int(v - t0):8d}" if v else "       -" for v in t[i][:14]))
+    print(f"kernel entry {int(t[0][14] - t0)}, exit {int(t[0][15] - t0)} (cycles relative to block 0 s_full)")
