@@ -3,8 +3,12 @@
 // qkv is the packed [T, 3H] output of the Wqkv GEMM (RoPE already applied): q | k | v column thirds,
 // 64 columns per head (HF:280-282); out is [T, H].
 //
-// One CTA = one (sequence, head, 128-query tile); two CTAs are resident per SM so that one CTA's
-// softmax overlaps the other's MMAs.  Warp roles (256 threads):
+// Work unit = one (sequence, head, 128-query tile).  The kernel is PERSISTENT: 2 CTAs per SM walk the tile
+// list with a grid stride, so TMEM allocation, barrier setup and the first TMA round trip are paid once per
+// CTA and the producer / MMA warps run ahead into the next tile while the softmax warps finish the current
+// one (a local-attention tile is only two key blocks long: launched one CTA per tile, more than half of its
+// ~11000 cycles were prologue and epilogue).  Two CTAs per SM so that one CTA's softmax overlaps the other's
+// MMAs.  Warp roles (256 threads):
 //   warps 0..3  softmax      ONE THREAD PER QUERY ROW (TMEM lane = row): tcgen05.ld the 128 scores of
 //                            the row, thread-local max / exp2 / sum (no shuffles), write P as packed
 //                            bf16 back to TMEM (tcgen05.st), rescale O in TMEM only when the running max
@@ -47,16 +51,14 @@ template <bool P_IN_TMEM>
 __global__ void __launch_bounds__(kFaThreads, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
                          const int32_t* __restrict__ cu_seqlens, const int H, const int half_window,
-                         long long* __restrict__ trace) {
-  // trace (tools/attn_check.py only; nullptr in the product): clock64() stamps of CTA (1,0,0), 16 slots per key
-  // block: softmax warp 0 [0 s_full seen, 1 scores read, 4 pv_done seen, 5 P published], MMA warp [6 S(i) issued,
-  // 7 PV(i) issued], softmax warp w < 3 [8+2w scores read, 9+2w P published]; block 0 slots 14 / 15 = kernel entry / exit.
+                         const int n_seqs, const int tiles_per_seq, long long* __restrict__ trace) {
+  // trace (tools/attn_check.py only; nullptr in the product): clock64() stamps of the first tile of CTA 1, 16 slots
+  // per key block: softmax warp 0 [0 s_full seen, 1 scores read, 4 pv_done seen, 5 P published], MMA warp
+  // [6 S(i) issued, 7 PV(i) issued], softmax warp w < 3 [8+2w scores read, 9+2w P published]; block 0 slots
+  // 14 / 15 = kernel entry / exit.
   using L = FaSmemLayout<P_IN_TMEM>;
-  const int seq = blockIdx.z, head = blockIdx.y;
-  const int begin = cu_seqlens[seq];
-  const int n = cu_seqlens[seq + 1] - begin;
-  const int q0 = blockIdx.x * kFaBlockM;
-  if (q0 >= n) return;  // CTA-uniform, before any barrier / TMEM allocation
+  const int heads = H / 64;
+  const int total_tiles = n_seqs * heads * tiles_per_seq;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -74,21 +76,40 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
   uint64_t* s_empty = s_full + 1;              // S(i) read into registers        (4 warp arrivals)
   uint64_t* p_full = s_empty + 1;              // P(i) written (+ O rescaled)     (4 warp arrivals)
   uint64_t* pv_done = p_full + 1;              // O += P(i).V(i) complete         (tcgen05.commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint64_t* q_empty = pv_done + 1;             // last S of a tile complete: Q may be overwritten (tcgen05.commit)
+  uint64_t* o_empty = q_empty + 1;             // O of a tile read by the epilogue (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const bool global = half_window < 0;
-  const bool tracing = trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  const bool trace_cta = trace != nullptr && blockIdx.x == 1 && lane == 0;
+  bool tracing = trace_cta;  // cleared after the CTA's first tile
 #define OPV_FA_STAMP(blk, slot) do { if (tracing) trace[(blk) * 16 + (slot)] = clock64(); } while (0)
   if (warp == 0) OPV_FA_STAMP(0, 14);  // kernel entry
 
-  // Key blocks of 128: global layers walk [0, n); local layers walk [q0 - w, q0 + 128 + w) -- the band of this
-  // query tile -- starting at an UNALIGNED key (TMA zero-fills rows before the tensor, rows of the previous
-  // sequence are masked), so a tile needs 2 blocks instead of the 3 that 128-aligned blocks would touch.
-  const int key_base = global ? 0 : q0 - half_window;
-  const int key_end = global ? n : min(n, q0 + kFaBlockM + half_window);
-  const int nb = (key_end - key_base + kFaBlockN - 1) / kFaBlockN;  // >= 1
+  // Tile t -> (sequence, head, query tile); consecutive t are consecutive query tiles of one (sequence, head), so
+  // the CTAs running at the same time share K / V in L2.  Key blocks of 128: global layers walk [0, n); local
+  // layers walk [q0 - w, q0 + 128 + w) -- the band of this query tile -- starting at an UNALIGNED key (TMA
+  // zero-fills rows before the tensor, rows of the previous sequence are masked), so a tile needs 2 blocks instead
+  // of the 3 that 128-aligned blocks would touch.  Every role decodes the same tiles and skips the empty ones.
+  struct Tile {
+    int begin, n, q0, head, key_base, nb;
+  };
+  auto decode = [&](const int t, Tile& tile) -> bool {
+    const int qt = t % tiles_per_seq;
+    const int sh = t / tiles_per_seq;
+    const int seq = sh / heads;
+    tile.head = sh - seq * heads;
+    tile.begin = cu_seqlens[seq];
+    tile.n = cu_seqlens[seq + 1] - tile.begin;
+    tile.q0 = qt * kFaBlockM;
+    if (tile.q0 >= tile.n) return false;
+    tile.key_base = global ? 0 : tile.q0 - half_window;
+    const int key_end = global ? tile.n : min(tile.n, tile.q0 + kFaBlockM + half_window);
+    tile.nb = (key_end - tile.key_base + kFaBlockN - 1) / kFaBlockN;  // >= 1
+    return true;
+  };
 
   if (warp == 4 && lane == 0) tma_prefetch_desc(&tm_qkv);
   if (warp == 5 && lane == 0) {
@@ -103,6 +124,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
     mbar_init(s_empty, 4);
     mbar_init(p_full, 4);
     mbar_init(pv_done, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_empty, 4);
     fence_mbar_init();
   }
   if (warp == 6) {
@@ -119,24 +142,33 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
     if (warp == 4) {
       // ------------------------------ TMA producer ------------------------------
       if (lane == 0) {
-        const int row0 = begin + q0;
-        mbar_expect_tx(q_full, kFaTileBytes);
-        tma_load_2d(sQ, &tm_qkv, q_full, head * 64, row0);
-        // consumption order of the MMA warp: K0, K1, V0, K2, V1, ...
-        for (int i = 0; i <= nb; ++i) {
-          if (i < nb) {
-            const int st = i % kFaKvStages;
-            mbar_wait(&k_empty[st], ((i / kFaKvStages) & 1) ^ 1);
-            mbar_expect_tx(&k_full[st], kFaTileBytes);
-            tma_load_2d(sK + st * kFaTileBytes, &tm_qkv, &k_full[st], H + head * 64, begin + key_base + i * kFaBlockN);
+        uint32_t tiles_done = 0, kc = 0, vc = 0;  // running counts -> ring stage and barrier parity
+        Tile tl;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          if (!decode(t, tl)) continue;
+          if (tiles_done > 0) mbar_wait(q_empty, (tiles_done - 1) & 1);  // previous tile's S MMAs have read Q
+          mbar_expect_tx(q_full, kFaTileBytes);
+          tma_load_2d(sQ, &tm_qkv, q_full, tl.head * 64, tl.begin + tl.q0);
+          // consumption order of the MMA warp: K0, K1, V0, K2, V1, ...
+          for (int i = 0; i <= tl.nb; ++i) {
+            if (i < tl.nb) {
+              const uint32_t st = kc % kFaKvStages;
+              mbar_wait(&k_empty[st], ((kc / kFaKvStages) & 1) ^ 1);
+              mbar_expect_tx(&k_full[st], kFaTileBytes);
+              tma_load_2d(sK + st * kFaTileBytes, &tm_qkv, &k_full[st], H + tl.head * 64,
+                          tl.begin + tl.key_base + i * kFaBlockN);
+              ++kc;
+            }
+            if (i >= 1) {
+              const uint32_t st = vc % kFaKvStages;
+              mbar_wait(&v_empty[st], ((vc / kFaKvStages) & 1) ^ 1);
+              mbar_expect_tx(&v_full[st], kFaTileBytes);
+              tma_load_2d(sV + st * kFaTileBytes, &tm_qkv, &v_full[st], 2 * H + tl.head * 64,
+                          tl.begin + tl.key_base + (i - 1) * kFaBlockN);
+              ++vc;
+            }
           }
-          if (i >= 1) {
-            const int j = i - 1, st = j % kFaKvStages;
-            mbar_wait(&v_empty[st], ((j / kFaKvStages) & 1) ^ 1);
-            mbar_expect_tx(&v_full[st], kFaTileBytes);
-            tma_load_2d(sV + st * kFaTileBytes, &tm_qkv, &v_full[st], 2 * H + head * 64,
-                        begin + key_base + j * kFaBlockN);
-          }
+          ++tiles_done;
         }
       }
     } else if (warp == 5) {
@@ -145,10 +177,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
       constexpr uint32_t idesc_o = umma_idesc_bf16_f32_bmn(kFaBlockM, 64);     // P.V: V is MN-major
       const uint32_t t_s = tmem_base, t_p = tmem_base + 128, t_o = tmem_base + 192;
       const uint32_t q_addr = smem_u32(sQ);
-      auto issue_s = [&](int i) {  // S(i) = Q . K(i)^T
-        const int st = i % kFaKvStages;
-        mbar_wait(&k_full[st], (i / kFaKvStages) & 1);
-        if (i > 0) mbar_wait(s_empty, (i - 1) & 1);
+      uint32_t tiles_done = 0, sc = 0, pc = 0;  // running counts of S / PV issues -> ring stage and barrier parity
+      auto issue_s = [&](const int i, const bool last_of_tile) {  // S(i) = Q . K(i)^T
+        const uint32_t st = sc % kFaKvStages;
+        mbar_wait(&k_full[st], (sc / kFaKvStages) & 1);
+        if (sc > 0) mbar_wait(s_empty, (sc - 1) & 1);  // the softmax warps have read the previous S
         tc_fence_after();
         if (elect_one()) {
           const uint32_t k_addr = smem_u32(sK + st * kFaTileBytes);
@@ -158,46 +191,61 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
                          k != 0 ? 1u : 0u);
           umma_commit(&k_empty[st]);
           umma_commit(s_full);
+          if (last_of_tile) umma_commit(q_empty);
           OPV_FA_STAMP(i, 6);
         }
         __syncwarp();
+        ++sc;
       };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int i = 0; i < nb; ++i) {
-        if (i + 1 < nb) issue_s(i + 1);
-        const int st = i % kFaKvStages;
-        mbar_wait(&v_full[st], (i / kFaKvStages) & 1);
-        mbar_wait(p_full, i & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t v_addr = smem_u32(sV + st * kFaTileBytes);
+      Tile tl;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        if (!decode(t, tl)) continue;
+        mbar_wait(q_full, tiles_done & 1);
+        issue_s(0, tl.nb == 1);
+        for (int i = 0; i < tl.nb; ++i) {
+          if (i + 1 < tl.nb) issue_s(i + 1, i + 2 == tl.nb);
+          const uint32_t st = pc % kFaKvStages;
+          mbar_wait(&v_full[st], (pc / kFaKvStages) & 1);
+          mbar_wait(p_full, pc & 1);
+          if (i == 0 && tiles_done > 0) mbar_wait(o_empty, (tiles_done - 1) & 1);  // epilogue has read the previous O
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t v_addr = smem_u32(sV + st * kFaTileBytes);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // 16 keys per MMA: two 8-key groups of 1024 B
-            const uint64_t b_desc = umma_desc_mn_sw128(v_addr + k * 2048);
-            const uint32_t acc = (i | k) != 0 ? 1u : 0u;
-            if constexpr (P_IN_TMEM) {
-              umma_bf16_ts(t_o, t_p + k * 8, b_desc, idesc_o, acc);
-            } else {
-              const uint32_t p_addr = smem_u32(sP) + (k >> 2) * kFaTileBytes + (k & 3) * 32;
-              umma_bf16_ss(t_o, umma_desc_k_sw128(p_addr), b_desc, idesc_o, acc);
+            for (int k = 0; k < 8; ++k) {  // 16 keys per MMA: two 8-key groups of 1024 B
+              const uint64_t b_desc = umma_desc_mn_sw128(v_addr + k * 2048);
+              const uint32_t acc = (i | k) != 0 ? 1u : 0u;
+              if constexpr (P_IN_TMEM) {
+                umma_bf16_ts(t_o, t_p + k * 8, b_desc, idesc_o, acc);
+              } else {
+                const uint32_t p_addr = smem_u32(sP) + (k >> 2) * kFaTileBytes + (k & 3) * 32;
+                umma_bf16_ss(t_o, umma_desc_k_sw128(p_addr), b_desc, idesc_o, acc);
+              }
             }
+            umma_commit(&v_empty[st]);
+            umma_commit(pv_done);
+            OPV_FA_STAMP(i, 7);
           }
-          umma_commit(&v_empty[st]);
-          umma_commit(pv_done);
-          OPV_FA_STAMP(i, 7);
+          __syncwarp();
+          ++pc;
         }
-        __syncwarp();
+        ++tiles_done;
+        tracing = false;
       }
     }
   } else {
     // ------------------------------ softmax warps (one thread per query row) ----
     setmaxnreg_inc<216>();
     const int r_tile = warp * 32 + lane;  // row inside the tile == TMEM lane
-    const int row = q0 + r_tile;          // row inside the sequence
     const uint32_t t_s = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     const uint32_t t_p = t_s + 128, t_o = t_s + 192;
     const float scale_log2 = 0.125f * 1.44269504088896340736f;  // head_dim^-0.5 * log2(e)
+    uint32_t tiles_done = 0, bc = 0;  // running count of key blocks -> barrier parity
+    Tile tl;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    if (!decode(t, tl)) continue;
+    const int begin = tl.begin, n = tl.n, q0 = tl.q0, head = tl.head, key_base = tl.key_base, nb = tl.nb;
+    const int row = q0 + r_tile;          // row inside the sequence
     float m_run = -CUDART_INF_F, l_run = 0.f;
     // keys this row may attend to: [k_lo, k_lo + k_span]; for the warp's 32 rows: keys every row sees
     // [all_lo, all_hi] and keys some row sees [any_lo, any_hi]
@@ -210,8 +258,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
     const int any_lo = global ? 0 : max(row_first - half_window, 0);
     const int any_hi = global ? n - 1 : min(row_last + half_window, n - 1);
 
-    for (int i = 0; i < nb; ++i) {
-      mbar_wait(s_full, i & 1);
+    for (int i = 0; i < nb; ++i, ++bc) {
+      mbar_wait(s_full, bc & 1);
       tc_fence_after();
       if (warp == 0) OPV_FA_STAMP(i, 0);
       uint32_t sr[128];
@@ -312,7 +360,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
       }
 
       if (i > 0) {
-        mbar_wait(pv_done, (i - 1) & 1);  // O holds blocks < i and the P buffer is free again
+        mbar_wait(pv_done, (bc - 1) & 1);  // O holds blocks < i and the P buffer is free again
         tc_fence_after();
         if (warp == 0) OPV_FA_STAMP(i, 4);
         if (__any_sync(0xffffffffu, upd)) {
@@ -343,10 +391,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
     }
 
     // epilogue: O / l -> bf16 -> out[begin + row, head*64 : head*64+64]
-    mbar_wait(pv_done, (nb - 1) & 1);
+    mbar_wait(pv_done, (bc - 1) & 1);
     tc_fence_after();
     uint32_t orr[64];
     tmem_ld_32x32b_x64(t_o, orr);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(o_empty);  // the next tile's first P.V may overwrite O
     if (row < n) {
       const float inv = 1.0f / l_run;
       uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(begin) + row) * H + head * 64);
@@ -360,10 +411,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
         dst[g] = u;
       }
     }
+    ++tiles_done;
+    tracing = false;
+    }  // tile loop
   }
 
   tc_fence_before();
   __syncthreads();
+  tracing = trace_cta;
   if (warp == 0) OPV_FA_STAMP(0, 15);  // all roles done (before the TMEM release)
 #undef OPV_FA_STAMP
   if (warp == 6) tmem_dealloc(tmem_base, kFaTmemCols);

@@ -277,13 +277,17 @@ int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, i
   const int H = heads * 64;
   if (dtype == OPV_DTYPE_BF16 && g_attention_impl != 0) {
     if (!tm_qkv) return fail(OPV_ERR_INVALID_ARGUMENT, "tcgen05 attention needs the qkv tensor map");
-    dim3 grid((max_seqlen + opv::kFaBlockM - 1) / opv::kFaBlockM, heads, n_seqs);
+    // persistent: two CTAs per SM walk the (sequence, head, query tile) list with a grid stride
+    const int tiles_per_seq = (max_seqlen + opv::kFaBlockM - 1) / opv::kFaBlockM;
+    const int64_t total_tiles = static_cast<int64_t>(n_seqs) * heads * tiles_per_seq;
+    if (total_tiles > 0x7fffffffLL) return fail(OPV_ERR_UNSUPPORTED, "too many attention tiles for one launch");
+    const int grid = static_cast<int>(total_tiles < 2 * g_num_sms ? total_tiles : 2 * g_num_sms);
     if (g_attention_impl == 1)
       opv::attention_tcgen05_kernel<true><<<grid, opv::kFaThreads, opv::FaSmemLayout<true>::kTotal, s>>>(
-          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, g_attention_trace);
+          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq, g_attention_trace);
     else
       opv::attention_tcgen05_kernel<false><<<grid, opv::kFaThreads, opv::FaSmemLayout<false>::kTotal, s>>>(
-          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, g_attention_trace);
+          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq, g_attention_trace);
     OPV_LAUNCH_CHECK("attention_tcgen05_kernel");
   } else if (dtype == OPV_DTYPE_BF16) {
     dim3 grid((max_seqlen + opv::kAttBlockM - 1) / opv::kAttBlockM, heads, n_seqs);
