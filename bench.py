@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-pairs", type=int, default=32, help="pairs in the bounded CPU-baseline sample")
     ap.add_argument("--ref-pairs-per-step", type=int, default=4)
+    ap.add_argument("--set-option", action="append", default=[], metavar="NAME=VALUE",
+                    help="library tuning switch for A/B runs (opv_set_option), e.g. zigzag=0")
     return ap.parse_args()
 
 
@@ -206,6 +208,12 @@ def main() -> None:
 
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if args.set_option:
+        from open_provence_b200 import ops
+
+        for item in args.set_option:
+            name, _, value = item.partition("=")
+            ops.set_option(name, int(value))
     cfg = syn.backbone_config(args.model)
     sd = syn.random_state_dict(cfg, seed=0)
     eng = Engine(cfg, sd, device=dev, dtype=args.dtype, num_labels=1)
