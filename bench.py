@@ -136,6 +136,8 @@ def dist_setup(args):
     if world > 1:
         import torch.distributed as dist
 
+        # NCCL writes its version / debug lines to stdout by default; rank 0's stdout carries the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     return world, rank, local
