@@ -66,3 +66,44 @@ def test_family_bf16_close(family):
     assert np.isfinite(prune).all() and np.isfinite(rank).all()
     # bf16 operands (2^-9 relative rounding) with fp32 accumulation / residual / LN / softmax
     assert e_rank < 2e-2 and e_prune < 1e-2 * scale
+
+
+def test_maximum_sequence_length_8192(tiny_ckpt_dir, tiny_config):
+    """One block at max_position_embeddings (8192 tokens: 64 key blocks per query tile, RoPE positions up to 8191
+    with theta 160000 / 10000) next to a 4097-token one, against the reference's fp64 forward on the tiny golden
+    checkpoint (tests/golden/make_golden_long.py)."""
+    from safetensors.torch import load_file
+
+    golden = np.load(tiny_ckpt_dir.parent / "forward_long_tiny.npz")
+    sd = load_file(str(tiny_ckpt_dir / "model.safetensors"))
+    lengths = golden["lengths"].tolist()
+    ids = torch.from_numpy(golden["input_ids"]).to("cuda")
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lengths)]), dtype=torch.int32, device="cuda")
+    ref_rank, ref_prune = golden["ranking_logits_f64"], golden["pruning_logits_f64"]
+    scale = max(1.0, np.abs(ref_prune).max())
+    for dtype, tol_rank, tol_prune in (("fp32", 1e-5, 2e-5 * scale), ("bf16", 2e-2, 1e-2 * scale)):
+        eng = Engine(tiny_config["base_model_config"], sd, device="cuda", dtype=dtype, num_labels=1)
+        prune, rank = eng.forward_packed(ids, cu, max(lengths))
+        torch.cuda.synchronize()
+        e_rank = np.abs(rank.cpu().double().numpy() - ref_rank).max()
+        e_prune = np.abs(prune.cpu().double().numpy() - ref_prune).max()
+        print(f"S=8192 {dtype} engine vs fp64 reference: rank {e_rank:.2e} prune {e_prune:.2e} (|prune| max {scale:.1f})")
+        assert e_rank < tol_rank and e_prune < tol_prune
+
+
+def test_empty_and_single_token_batches():
+    cfg = syn.backbone_config("tiny")
+    sd = syn.random_state_dict(cfg, seed=2)
+    eng = Engine(cfg, sd, device="cuda", dtype="bf16", num_labels=1)
+    empty_ids = torch.zeros(0, dtype=torch.int32, device="cuda")
+    prune, rank = eng.forward_packed(empty_ids, torch.zeros(1, dtype=torch.int32, device="cuda"), 1)
+    assert prune.shape == (0, 2) and rank.shape == (0, 1)
+    # 300 one-token blocks: every sequence is its own CLS row
+    ids = torch.arange(3, 303, dtype=torch.int32, device="cuda") % cfg["vocab_size"]
+    cu = torch.arange(0, 301, dtype=torch.int32, device="cuda")
+    prune, rank = eng.forward_packed(ids.contiguous(), cu, 1)
+    torch.cuda.synchronize()
+    w64 = {k: v.double().numpy() for k, v in sd.items()}
+    ref_rank, ref_prune = onp.forward_batch([[int(t)] for t in ids.cpu().tolist()[:5]], w64, cfg)
+    assert np.abs(rank[:5].cpu().double().numpy() - ref_rank).max() < 2e-2
+    assert torch.isfinite(prune).all() and torch.isfinite(rank).all()
