@@ -614,12 +614,16 @@ class OpenProvenceModel:
         return prefix, first
 
     # ------------------------------------------------------------------ process(): planning
-    def _plan_contexts(self, queries, contexts, titles, splitter: SentenceSplitter, strip: bool, timing: dict):
-        """Sentences for every (query, context) pair, then ONE batched tokenizer call for all of them."""
+    def _plan_contexts(self, queries, contexts, titles, splitter: SentenceSplitter, strip: bool, timing: dict,
+                       pairs: Sequence[tuple[int, int]] | None = None, query_tokens: list | None = None):
+        """Sentences for every (query, context) pair -- or for ``pairs`` only -- then ONE batched tokenizer call
+        for all of them."""
         plans: list[_ContextPlan] = []
         t_collect = t_norm = 0.0
-        for qi in range(len(queries)):
-            for ci, entry in enumerate(contexts[qi]):
+        if pairs is None:
+            pairs = [(qi, ci) for qi in range(len(queries)) for ci in range(len(contexts[qi]))]
+        for qi, ci in pairs:
+            for entry in (contexts[qi][ci],):
                 if isinstance(entry, list):
                     manual = [str(s) for s in entry if str(s).strip()]
                     text = "".join(manual)
@@ -642,7 +646,8 @@ class OpenProvenceModel:
             p.token_lists = flat_tokens[at : at + len(p.sentences)]
             at += len(p.sentences)
             p.prefix_token_counts = [len(t) for t in p.token_lists[: len(p.prefix_sentences)]]
-        query_tokens = [[int(t) for t in self.tokenizer.encode(q, add_special_tokens=False)] for q in queries]
+        if query_tokens is None:
+            query_tokens = [[int(t) for t in self.tokenizer.encode(q, add_special_tokens=False)] for q in queries]
         timing["sentence_collect_seconds"] += t_collect
         timing["sentence_normalize_seconds"] += t_norm
         timing["tokenize_seconds"] += perf_counter() - t0
@@ -792,7 +797,7 @@ class OpenProvenceModel:
         results do not depend on it.  ``preprocess_workers`` / ``preprocess_batch_size`` /
         ``torch_dataloader_kwargs`` / progress flags are accepted for signature compatibility: host
         preprocessing here is one batched tokenizer call, not a DataLoader of per-context jobs."""
-        del show_progress, show_inference_progress, enable_warnings, preprocess_workers, preprocess_batch_size
+        del show_progress, show_inference_progress, enable_warnings, preprocess_workers
         del torch_dataloader_kwargs
         if self._scorer is None:
             raise RuntimeError("this OpenProvenceModel has no engine (constructed without weights)")
@@ -814,19 +819,57 @@ class OpenProvenceModel:
         max_fragment_tokens = max(16, self.max_length - 2) if respect_sentence_boundaries else max(16, self.max_length // 2)
         sep_len = len(self.tokenizer.encode(getattr(self.tokenizer, "sep_token", None) or "", add_special_tokens=False))
 
-        plans, query_tokens = self._plan_contexts(queries, contexts, titles, splitter, strip_sentences, timing)
-        self._fragmentize(plans, max_fragment_tokens, strip_sentences, respect_sentence_boundaries, timing)
-        preprocess_time = sum(timing.values())
-        t0 = perf_counter()
-        table = self._build_table(plans, query_tokens, sep_len)
-        assembly_time = perf_counter() - t0
+        # Host preparation (sentences -> tokens -> fragments -> packed block table) of chunk k+1 runs in a worker
+        # thread while the device scores chunk k: the tokenizer releases the GIL, and so does this thread while it
+        # waits for the GPU.  (The reference streams its jobs through a DataLoader for the same reason,
+        # standalone:3510-3605.)  One chunk when the input is small.
+        all_pairs = [(qi, ci) for qi in range(len(queries)) for ci in range(len(contexts[qi]))]
+        chunk_size = max(1, int(preprocess_batch_size)) if preprocess_batch_size else 64
+        chunks = [all_pairs[i : i + chunk_size] for i in range(0, len(all_pairs), chunk_size)] or [[]]
+        query_tokens = [[int(t) for t in self.tokenizer.encode(q, add_special_tokens=False)] for q in queries]
+        stage = {"assembly": 0.0, "inference": 0.0}
 
-        t0 = perf_counter()
+        def prepare(pairs_k):
+            t_local = {k: 0.0 for k in timing}
+            plans_k, _ = self._plan_contexts(queries, contexts, titles, splitter, strip_sentences, t_local,
+                                             pairs=pairs_k, query_tokens=query_tokens)
+            self._fragmentize(plans_k, max_fragment_tokens, strip_sentences, respect_sentence_boundaries, t_local)
+            t0 = perf_counter()
+            table_k = self._build_table(plans_k, query_tokens, sep_len)
+            return plans_k, table_k, t_local, perf_counter() - t0
+
         if hasattr(self._scorer, "max_tokens"):
             self._scorer.max_tokens = max(131072, batch_size * max(self.max_length, 1))
-        scored = self._scorer.run(table, threshold) if table.n_blocks else {
-            "rank_score": np.zeros(0, np.float32), "sent_prob": np.zeros(0), "keep": np.zeros(0, bool)}
-        inference_time = perf_counter() - t0
+        plans: list[_ContextPlan] = []
+        parts: list[dict[str, np.ndarray]] = []
+        block_base = sentence_base = 0
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(prepare, chunks[0])
+            for k in range(len(chunks)):
+                plans_k, table_k, t_local, t_asm = pending.result()
+                if k + 1 < len(chunks):
+                    pending = pool.submit(prepare, chunks[k + 1])
+                for key, value in t_local.items():
+                    timing[key] += value
+                stage["assembly"] += t_asm
+                t0 = perf_counter()
+                if table_k.n_blocks:
+                    parts.append(self._scorer.run(table_k, threshold))
+                stage["inference"] += perf_counter() - t0
+                for p in plans_k:  # chunk-local slots -> positions in the concatenated result arrays
+                    p.block_slots = [b + block_base for b in p.block_slots]
+                    p.sentence_base += sentence_base
+                block_base += table_k.n_blocks
+                sentence_base += table_k.n_sentences
+                plans.extend(plans_k)
+        preprocess_time = sum(timing.values())
+        assembly_time, inference_time = stage["assembly"], stage["inference"]
+        if parts:
+            scored = {key: np.concatenate([part[key] for part in parts]) for key in ("rank_score", "sent_prob", "keep")}
+        else:
+            scored = {"rank_score": np.zeros(0, np.float32), "sent_prob": np.zeros(0), "keep": np.zeros(0, bool)}
 
         t0 = perf_counter()
         per_query = self._postprocess(

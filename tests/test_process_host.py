@@ -103,6 +103,25 @@ def test_process_matches_reference(name, process_golden, tiny_ckpt_dir, tiny_tok
     assert set(result["timing"]) == set(result["performance_trace"].as_dict())
 
 
+@pytest.mark.parametrize("name", ["str_list", "nested", "explicit_titles", "multi_block", "reorder_topk", "empty_context"])
+def test_chunked_host_pipeline_gives_the_same_result(name, process_golden, tiny_ckpt_dir, tiny_tokenizer):
+    """One context per host-preparation chunk (worker thread prepares chunk k+1 while chunk k is scored) must
+    reproduce the reference result exactly, like the single-chunk run above."""
+    case = next(c for c in process_golden["cases"] if c["name"] == name)
+    model, scorer = _model(tiny_ckpt_dir, tiny_tokenizer, case)
+    kwargs = dict(case["kwargs"])
+    kwargs["sentence_splitter"] = simple_sentence_splitter
+    kwargs["preprocess_batch_size"] = 1
+    result = model.process(**kwargs)
+    golden = case["result"]
+    assert sorted(scorer.seen) == sorted(tuple(b["ids"]) for b in case["blocks"])
+    for key in ("pruned_context", "kept_sentences", "removed_sentences", "title"):
+        assert result[key] == golden[key]
+    _approx_nested(result["compression_rate"], golden["compression_rate"], 1e-9)
+    _approx_nested(result["reranking_score"], golden["reranking_score"], 1e-6)
+    _approx_nested(result["sentence_probabilities"], golden["sentence_probabilities"], 1e-6)
+
+
 def test_process_default_result_keys(process_golden, tiny_ckpt_dir, tiny_tokenizer):
     case = next(c for c in process_golden["cases"] if c["name"] == "str_str")
     model, _ = _model(tiny_ckpt_dir, tiny_tokenizer, case)
