@@ -42,9 +42,7 @@ def main():
     t0 = time.perf_counter()
     out = model.process(**kw)
     dt = time.perf_counter() - t0
-    n_blocks = model._scorer.last_n_blocks if hasattr(model._scorer, "last_n_blocks") else -1
-    print(f"{name}: {n_ctx} contexts, max_length {max_length}, {n_blocks} blocks: {dt * 1e3:.1f} ms -> "
-          f"{n_ctx / dt:.0f} contexts/s, {n_blocks / dt:.0f} blocks/s end to end")
+    print(f"{name}: {n_ctx} contexts, max_length {max_length}: {dt * 1e3:.1f} ms -> {n_ctx / dt:.0f} contexts/s end to end")
     print({k: round(v, 4) for k, v in out["timing"].items()})
     kept = sum(len(p) for p in out["pruned_context"])
     print(f"pruned characters kept: {kept} of {sum(len(c) for c in contexts)}")
