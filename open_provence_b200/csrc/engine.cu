@@ -99,6 +99,8 @@ int g_attention_impl = 1;
 long long* g_attention_trace = nullptr;  // device buffer for clock64() stamps (tools/attn_check.py); nullptr in the product
 // bf16 GEMM with N % 256 == 0: 1 = CTA-pair kernel (cta_group::2, 256 x 256 tiles), 0 = single-CTA kernel
 int g_gemm_pair = 1;
+// ROPE GEMM: 1 = a cluster finishes all column tiles of a row block before the next row block (cos|sin staged once)
+int g_gemm_group_rows = 1;
 
 template <int BLOCK_N, int EPI>
 int set_gemm_attr() {
@@ -158,12 +160,15 @@ int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUten
 template <int EPI>
 int launch_gemm_pair(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_c,
                      const opv::GemmEpilogueArgs& ep, int64_t M, int N, int K, cudaStream_t stream) {
-  const int64_t tiles = ((M + 2 * opv::kGemmBlockM - 1) / (2 * opv::kGemmBlockM)) * (N / 256);
+  const int64_t pairs_m = (M + 2 * opv::kGemmBlockM - 1) / (2 * opv::kGemmBlockM);
+  const int64_t tiles = pairs_m * (N / 256);
   const int max_clusters = g_num_sms / 2;
   const int clusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
+  opv::GemmEpilogueArgs ep_launch = ep;
+  ep_launch.group_rows = (EPI == opv::kEpiRope && g_gemm_group_rows && pairs_m >= 4 * clusters) ? 1 : 0;
   opv::gemm_bf16_tcgen05_pair_kernel<EPI>
-      <<<2 * clusters, opv::gemm_threads(EPI), opv::GemmPairSmemLayout<EPI>::kTotal, stream>>>(tm_a, tm_b, tm_c, ep, (int)M,
-                                                                                          N, K);
+      <<<2 * clusters, opv::gemm_threads(EPI), opv::GemmPairSmemLayout<EPI>::kTotal, stream>>>(tm_a, tm_b, tm_c, ep_launch,
+                                                                                          (int)M, N, K);
   OPV_LAUNCH_CHECK("gemm_bf16_tcgen05_pair_kernel");
   return OPV_OK;
 }
@@ -801,6 +806,10 @@ int opv_set_option(const char* name, int64_t value) {
   }
   if (strcmp(name, "attention_trace_ptr") == 0) {
     g_attention_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));
+    return OPV_OK;
+  }
+  if (strcmp(name, "gemm_group_rows") == 0) {
+    g_gemm_group_rows = value != 0;
     return OPV_OK;
   }
   if (strcmp(name, "gemm_pair") == 0) {

@@ -40,6 +40,10 @@ struct GemmEpilogueArgs {
   const float* cos;    // ROPE: [max_pos, 32]
   const float* sin;    // ROPE: [max_pos, 32]
   int32_t rope_cols;   // ROPE: output columns < rope_cols (= 2H: q and k) are rotated
+  // CTA-pair kernel, ROPE: 1 = a cluster takes ALL column tiles of a 256-row block before moving to its next row
+  // block, so the rows' cos|sin table lines are staged once per row block instead of once per rotated tile
+  // (set by the host when there are at least as many row blocks as clusters)
+  int32_t group_rows;
 };
 
 // ROPE epilogue: the cos|sin rows (2 x 128 B) of the tile's 128 tokens are staged in shared memory by
@@ -349,6 +353,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 // are counted on the even CTA's full barrier; tcgen05.commit multicasts the smem-slot / accumulator
 // hand-offs to both CTAs; each CTA's epilogue drains its own 128 TMEM lanes exactly as above.
 // --------------------------------------------------------------------------------------------------
+// u-th tile of the cluster `first` (of `step` clusters).  Default: tile index first + u * step over the
+// row-major [row block][column tile] list.  group_rows: all column tiles of row block first, then of first + step, ...
+__device__ __forceinline__ bool pair_tile(int u, int first, int step, int num_tiles, int num_pairs_m, int num_n,
+                                          int group_rows, int& m_pair, int& n_blk) {
+  if (group_rows) {
+    m_pair = first + (u / num_n) * step;
+    n_blk = u % num_n;
+    return m_pair < num_pairs_m;
+  }
+  const int tile = first + u * step;
+  m_pair = tile / num_n;
+  n_blk = tile % num_n;
+  return tile < num_tiles;
+}
+
 template <int EPI>
 struct GemmPairSmemLayout {
   static constexpr int kStageA = kGemmBlockM * kGemmBlockK * 2;  // 16 KB: this CTA's 128 rows of A
@@ -422,8 +441,9 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
     // ------------------------------ TMA producer (both CTAs) ------------------
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-      const int m_pair = tile / num_n, n_blk = tile % num_n;
+    for (int u = 0;; ++u) {
+      int m_pair, n_blk;
+      if (!pair_tile(u, first_tile, tile_step, num_tiles, num_pairs_m, num_n, ep.group_rows, m_pair, n_blk)) break;
       const int row0 = (m_pair * 2 + cta_rank) * kGemmBlockM;
       const int wrow0 = n_blk * BLOCK_N + cta_rank * 128;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -445,7 +465,9 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      for (int u = 0;; ++u) {
+        int m_pair, n_blk;
+        if (!pair_tile(u, first_tile, tile_step, num_tiles, num_pairs_m, num_n, ep.group_rows, m_pair, n_blk)) break;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // both CTAs' epilogues drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -480,11 +502,12 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
     ring.leader = ((warp - 2) & 3) == 0 && lane == 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-      const int m_pair = tile / num_n, n_blk = tile % num_n;
+    for (int u = 0;; ++u) {
+      int m_pair, n_blk;
+      if (!pair_tile(u, first_tile, tile_step, num_tiles, num_pairs_m, num_n, ep.group_rows, m_pair, n_blk)) break;
       const int m_blk = m_pair * 2 + cta_rank;
       if constexpr (EPI == kEpiRope) {
-        if (n_blk * BLOCK_N < ep.rope_cols) {
+        if (n_blk * BLOCK_N < ep.rope_cols && (!ep.group_rows || n_blk == 0)) {
           named_bar_sync(3, 256);
           rope_stage_rows(ep, rope_cs, threadIdx.x - 64, m_blk * kGemmBlockM, M);
           named_bar_sync(3, 256);

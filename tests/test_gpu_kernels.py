@@ -87,7 +87,7 @@ def _rope_ref(qkv: torch.Tensor, pos: torch.Tensor, cos: torch.Tensor, sin: torc
     return x.view(t, 3 * hidden)
 
 
-@pytest.mark.parametrize("m,hidden", [(333, 128), (1500, 256), (2000, 512)])
+@pytest.mark.parametrize("m,hidden", [(333, 128), (1500, 256), (2000, 512), (76033, 256)])  # last: row-grouped tile order
 def test_gemm_bf16_rope(m, hidden, gemm_kernel):
     a = _rand_bf16((m, hidden), 6)
     w = _rand_bf16((3 * hidden, hidden), 7, 0.05)
