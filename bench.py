@@ -42,6 +42,28 @@ UNIT = "pairs/s"
 THRESHOLD = 0.1
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout() -> None:
+    """From here on everything libraries print to stdout (NCCL's version banner, ...) goes to stderr; the ONE
+    JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -136,8 +158,6 @@ def dist_setup(args):
     if world > 1:
         import torch.distributed as dist
 
-        # NCCL writes its version / debug lines to stdout by default; rank 0's stdout carries the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.cuda.set_device(local)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     return world, rank, local
@@ -188,11 +208,12 @@ def run_reference(args, world: int, rank: int) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main() -> None:
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         # CPU only: no process group; under torchrun rank 0 alone runs it, with every host thread it can use
         # (torchrun exports OMP_NUM_THREADS=1, which would otherwise pin the baseline to one core)
@@ -398,7 +419,7 @@ def main() -> None:
         "profile_ms_per_step": profile_ms,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
