@@ -119,8 +119,9 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
                        void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Process-wide tuning switches (tests, profiling).  "attention_impl": bf16 attention kernel,
- * 0 = mma.sync flash kernel (v1), 1 = tcgen05 kernel with P in TMEM (default), 2 = tcgen05 kernel with P
- * staged through shared memory.  "attention_trace_ptr": device buffer for the clock64() timeline of
+ * 0 = mma.sync flash kernel (v1), 1 = tcgen05 (default: one softmax thread per query row for global layers, two
+ * per row for sliding-window layers), 2 = one thread per row with P staged through shared memory, 3 = two
+ * threads per row everywhere, 4 = one thread per row everywhere.  "attention_trace_ptr": device buffer for the clock64() timeline of
  * tools/attn_check.py (0 = off, the product setting). */
 int opv_set_option(const char* name, int64_t value);
 

@@ -14,6 +14,7 @@
 #include "../../include/opv.h"
 #include "attention.cuh"
 #include "attention_tcgen05.cuh"
+#include "attention_tcgen05_v3.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tcgen05.cuh"
@@ -94,7 +95,9 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 
 int g_num_sms = 0;
 bool g_attrs_set = false;
-// bf16 attention kernel: 0 = mma.sync v1, 1 = tcgen05 with P in TMEM (default), 2 = tcgen05 with P in smem
+// bf16 attention kernel: 0 = mma.sync v1, 1 = tcgen05 (default: one-thread-per-row kernel for global layers,
+// two-threads-per-row kernel for sliding-window layers), 2 = one-thread-per-row with P in smem,
+// 3 = two-threads-per-row everywhere, 4 = one-thread-per-row (P in TMEM) everywhere
 int g_attention_impl = 1;
 long long* g_attention_trace = nullptr;  // device buffer for clock64() stamps (tools/attn_check.py); nullptr in the product
 // bf16 GEMM with N % 256 == 0: 1 = CTA-pair kernel (cta_group::2, 256 x 256 tiles), 0 = single-CTA kernel
@@ -141,6 +144,8 @@ int ensure_device_setup() {
                                 opv::FaSmemLayout<true>::kTotal));
   OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 opv::FaSmemLayout<false>::kTotal));
+  OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                opv::Fa3SmemLayout::kTotal));
   g_attrs_set = true;
   return OPV_OK;
 }
@@ -287,7 +292,12 @@ int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, i
     const int64_t total_tiles = static_cast<int64_t>(n_seqs) * heads * tiles_per_seq;
     if (total_tiles > 0x7fffffffLL) return fail(OPV_ERR_UNSUPPORTED, "too many attention tiles for one launch");
     const int grid = static_cast<int>(total_tiles < 2 * g_num_sms ? total_tiles : 2 * g_num_sms);
-    if (g_attention_impl == 1)
+    // default (1): one softmax thread per row for global layers (649 vs 585 TFLOP/s at S = 2048), two threads per row
+    // for sliding-window layers (0.156 vs 0.176 ms per layer at 64 x 2048); 3 / 4 force one of them everywhere
+    if (g_attention_impl == 3 || (g_attention_impl == 1 && half_window >= 0))
+      opv::attention_tcgen05_v3_kernel<<<grid, opv::kFa3Threads, opv::Fa3SmemLayout::kTotal, s>>>(
+          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq);
+    else if (g_attention_impl == 1 || g_attention_impl == 4)
       opv::attention_tcgen05_kernel<true><<<grid, opv::kFaThreads, opv::FaSmemLayout<true>::kTotal, s>>>(
           *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq, g_attention_trace);
     else
@@ -800,7 +810,7 @@ int opv_op_attention(int32_t dtype, const void* d_qkv, void* d_out, const int32_
 int opv_set_option(const char* name, int64_t value) {
   if (!name) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_set_option: null name");
   if (strcmp(name, "attention_impl") == 0) {
-    if (value < 0 || value > 2) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_impl must be 0, 1 or 2");
+    if (value < 0 || value > 4) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_impl must be 0 .. 4");
     g_attention_impl = static_cast<int>(value);
     return OPV_OK;
   }

@@ -72,9 +72,6 @@ __device__ __forceinline__ void staging_write_row(uint8_t* buf, int r, const uin
         make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 // Epilogue-group state: which staging buffer is next and how many buffers the group owns.
 template <int NBUF>
