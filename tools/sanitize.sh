@@ -1,0 +1,6 @@
+#!/usr/bin/env bash
+# compute-sanitizer memcheck over the smoke forward (single-CTA GEMMs, both attention kernels) and one model-family
+# parity case (CTA-pair GEMMs).  Usage on the GPU box: bash tools/sanitize.sh
+set -u
+compute-sanitizer --tool memcheck --print-limit 5 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
+compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_families.py -m gpu -x -q -k "xsmall and bf16" 2>&1 | tail -4
