@@ -190,3 +190,27 @@ def test_device_scorer_guard_band_matches_exact_reference_procedure(model_fp32):
     assert abs(exact - thr) < 1e-6
     others = np.abs(first["sent_prob"] - thr) > 1e-5
     assert np.array_equal(second["keep"][others], (first["sent_prob"] > thr)[others])
+
+
+def test_raw_predictions_and_thresholds_on_the_engine(model_fp32, tiny_ckpt_dir):
+    """get_raw_predictions_batch / predict_with_thresholds end to end (fp32 engine) against the reference's recorded
+    results (tests/golden/make_golden_raw.py)."""
+    import json
+
+    golden = json.loads((tiny_ckpt_dir.parent / "raw_tiny.json").read_text())
+    saved = model_fp32.max_length
+    model_fp32.max_length = golden["max_length"]
+    try:
+        raws = model_fp32.get_raw_predictions_batch(golden["batch_queries"], golden["batch_contexts"])
+        sep = model_fp32.tokenizer.sep_token
+        for got, want, q, ctx in zip(raws, golden["raw_batch"], golden["batch_queries"], golden["batch_contexts"]):
+            n = len(model_fp32.tokenizer(q + sep + "".join(ctx), truncation=True, max_length=golden["max_length"])["input_ids"])
+            assert abs(got.ranking_score - want["ranking_score"]) < 1e-5
+            assert [list(r) for r in got.context_ranges] == want["context_ranges"]
+            np.testing.assert_allclose(got.pruning_probs[:n], want["pruning_probs"][:n], atol=1e-5)
+        for want in golden["thresholds"]:
+            got = model_fp32.predict_with_thresholds(golden["query"], golden["contexts"], [0.05, 0.1, 0.5],
+                                                     use_majority=want["use_majority"])
+            assert {str(k): v for k, v in got["predictions"].items()} == want["predictions"]
+    finally:
+        model_fp32.max_length = saved
