@@ -168,6 +168,75 @@ int opv_sentence_prune(const float* d_frag_mean, const int32_t* d_sent_offsets, 
                        int32_t n_sents, double threshold, double guard, double* d_sent_prob, uint8_t* d_keep,
                        uint8_t* d_near, void* stream);
 
+/* ---- host-side block assembly (no device work) -------------------------------------------------
+ *
+ * Replaces the per-token Python list handling between the tokenizer and the device in process():
+ *   _split_token_lists                 standalone:686-713     fragment windows of max_fragment_tokens
+ *   _decode_and_filter_fragments       standalone:846-894     windows whose decoded text is empty are dropped
+ *   _assemble_blocks_from_fragments    standalone:2222-2259   greedy packing, truncation (2082)
+ *   _prepare_block_inputs              standalone:2104-2184   head | query | mid | context | tail, context
+ *                                                             located by first occurrence, fragment ranges
+ *   _postprocess_contexts              standalone:3076-3080   prefix-token offset applied to the ranges
+ *                                      standalone:3094-3099   sentence -> fragment slots
+ * Input is the tokenizer output flattened into one int32 array; output is the packed table
+ * opv_forward_packed / opv_fragment_means / opv_sentence_prune consume.  All pointers are HOST pointers.
+ *
+ * The empty-text filter needs the tokenizer: the caller passes h_token_visible[id] = 1 for every token whose
+ * own decoded text contains a visible character.  A window with such a token cannot decode to nothing and is
+ * kept without decoding.  If some windows are not settled that way and h_frag_drop is NULL, the build stops
+ * after listing the windows (view.needs_decode = 1): the caller decodes the flagged ones, sets
+ * h_frag_drop[i] = 1 where the text is empty, and calls opv_pack_build again.
+ */
+typedef struct opv_pack_input {
+  int32_t abi_version;              /* must be OPV_ABI_VERSION */
+  int32_t max_length;               /* model.max_length (block capacity = max_length - 2, standalone:2235) */
+  int32_t max_fragment_tokens;      /* window length (standalone:3466-3470) */
+  int32_t keep_sentence_boundaries; /* respect_sentence_boundaries */
+  int32_t sep_len;                  /* len(tokenizer.encode(sep_token)) (standalone:2232) */
+  int32_t n_contexts;
+  int32_t n_queries;
+  int32_t vocab_size;               /* entries of h_token_visible */
+  int32_t n_head, n_mid, n_tail;    /* special tokens around query and context ([CLS] q [SEP] ctx [SEP]) */
+  const int32_t* h_head;
+  const int32_t* h_mid;
+  const int32_t* h_tail;
+  const int32_t* h_tokens;          /* sentence tokens of all contexts, concatenated */
+  const int64_t* h_sent_offsets;    /* [n_sentences + 1] into h_tokens */
+  const int64_t* h_ctx_sent_offsets;/* [n_contexts + 1] sentence range of every context */
+  const int32_t* h_ctx_query;       /* [n_contexts] query index */
+  const int32_t* h_ctx_prefix;      /* [n_contexts] number of leading title sentences */
+  const int32_t* h_query_tokens;    /* query tokens, concatenated */
+  const int64_t* h_query_offsets;   /* [n_queries + 1] */
+  const uint8_t* h_token_visible;   /* [vocab_size] or NULL (then every window needs the tokenizer) */
+  const uint8_t* h_frag_drop;       /* NULL on the first call; [n_raw_fragments] on the second */
+} opv_pack_input;
+
+typedef struct opv_pack_view {
+  int32_t needs_decode;             /* 1: only the h_raw_* arrays are valid; decode and call again */
+  int64_t n_raw_fragments;          /* windows before the filter, context-major */
+  int64_t n_uncertain;
+  const uint8_t* h_raw_uncertain;   /* [n_raw_fragments] 1 = not settled by h_token_visible */
+  const int64_t* h_raw_start;       /* [n_raw_fragments] offset into h_tokens */
+  const int32_t* h_raw_len;         /* [n_raw_fragments] */
+  int64_t n_blocks, n_tokens, n_slots, n_sentences, n_contexts;
+  const int32_t* h_ids;             /* [n_tokens] packed block ids */
+  const int64_t* h_block_offsets;   /* [n_blocks + 1] (cu_seqlens) */
+  const int32_t* h_block_context;   /* [n_blocks] */
+  const int32_t* h_frag_block;      /* [n_slots] block of every fragment slot */
+  const int32_t* h_frag_local;      /* [n_slots, 2] block-local [start, end) */
+  const int32_t* h_sent_slot_offsets; /* [n_sentences + 1] CSR */
+  const int32_t* h_sent_slot_index; /* fragment slots of each sentence */
+  const int64_t* h_ctx_block_offsets; /* [n_contexts + 1] blocks of every context */
+} opv_pack_view;
+
+typedef void* opv_pack_handle;
+
+/* Build the packed table (or, with needs_decode, the window list).  The handle owns the arrays. */
+int opv_pack_build(const opv_pack_input* in, opv_pack_handle* out);
+/* Pointers into the handle's arrays; valid until opv_pack_destroy. */
+int opv_pack_view_get(opv_pack_handle handle, opv_pack_view* view);
+int opv_pack_destroy(opv_pack_handle handle);
+
 /* ---- single-op entry points (unit tests, profiling) ------------------------------------------- */
 
 typedef enum opv_epilogue {

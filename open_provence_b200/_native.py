@@ -75,6 +75,58 @@ class OpvWeights(C.Structure):
     ]
 
 
+class OpvPackInput(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("max_length", C.c_int32),
+        ("max_fragment_tokens", C.c_int32),
+        ("keep_sentence_boundaries", C.c_int32),
+        ("sep_len", C.c_int32),
+        ("n_contexts", C.c_int32),
+        ("n_queries", C.c_int32),
+        ("vocab_size", C.c_int32),
+        ("n_head", C.c_int32),
+        ("n_mid", C.c_int32),
+        ("n_tail", C.c_int32),
+        ("h_head", C.c_void_p),
+        ("h_mid", C.c_void_p),
+        ("h_tail", C.c_void_p),
+        ("h_tokens", C.c_void_p),
+        ("h_sent_offsets", C.c_void_p),
+        ("h_ctx_sent_offsets", C.c_void_p),
+        ("h_ctx_query", C.c_void_p),
+        ("h_ctx_prefix", C.c_void_p),
+        ("h_query_tokens", C.c_void_p),
+        ("h_query_offsets", C.c_void_p),
+        ("h_token_visible", C.c_void_p),
+        ("h_frag_drop", C.c_void_p),
+    ]
+
+
+class OpvPackView(C.Structure):
+    _fields_ = [
+        ("needs_decode", C.c_int32),
+        ("n_raw_fragments", C.c_int64),
+        ("n_uncertain", C.c_int64),
+        ("h_raw_uncertain", C.c_void_p),
+        ("h_raw_start", C.c_void_p),
+        ("h_raw_len", C.c_void_p),
+        ("n_blocks", C.c_int64),
+        ("n_tokens", C.c_int64),
+        ("n_slots", C.c_int64),
+        ("n_sentences", C.c_int64),
+        ("n_contexts", C.c_int64),
+        ("h_ids", C.c_void_p),
+        ("h_block_offsets", C.c_void_p),
+        ("h_block_context", C.c_void_p),
+        ("h_frag_block", C.c_void_p),
+        ("h_frag_local", C.c_void_p),
+        ("h_sent_slot_offsets", C.c_void_p),
+        ("h_sent_slot_index", C.c_void_p),
+        ("h_ctx_block_offsets", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/opv.h declares
 SIGNATURES = {
     "opv_last_error": (C.c_char_p, []),
@@ -101,6 +153,9 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
          C.c_void_p],
     ),
+    "opv_pack_build": (C.c_int, [C.POINTER(OpvPackInput), C.POINTER(C.c_void_p)]),
+    "opv_pack_view_get": (C.c_int, [C.c_void_p, C.POINTER(OpvPackView)]),
+    "opv_pack_destroy": (C.c_int, [C.c_void_p]),
     "opv_op_gemm": (
         C.c_int,
         [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,

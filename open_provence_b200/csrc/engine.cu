@@ -394,6 +394,9 @@ static WorkspaceLayout workspace_layout(const opv_engine* e, int64_t T, int64_t 
   return l;
 }
 
+// host_pack.cu reports errors through the same thread-local string
+void opv_detail_set_error(const char* message) { g_last_error = message ? message : ""; }
+
 extern "C" {
 
 const char* opv_last_error(void) { return g_last_error.c_str(); }

@@ -27,6 +27,7 @@ from typing import Any
 import numpy as np
 import torch
 
+from . import host_pack
 from .config import DEFAULT_PROCESS_THRESHOLD, OpenProvenceConfig
 from .host_text import (
     Fragment,
@@ -103,6 +104,8 @@ class _ContextPlan:
     blocks: list[list[Fragment]] = field(default_factory=list)
     block_slots: list[int] = field(default_factory=list)  # indices into BlockTable.block_ids
     sentence_base: int = 0  # first sentence slot in the BlockTable CSR
+    n_fragments: int = 0  # after the empty-fragment filter
+    n_blocks: int = 0
 
 
 def _is_seq(value: Any) -> bool:
@@ -760,7 +763,45 @@ class OpenProvenceModel:
             for s in range(len(p.sentences)):
                 table.sent_frag_index.extend(per_sentence.get(s, []))
                 table.sent_offsets.append(len(table.sent_frag_index))
+            p.n_fragments, p.n_blocks = len(p.fragments), len(p.blocks)
         return table
+
+    def _pack_template(self):
+        """Special-token template for the native packer, derived once per tokenizer state."""
+        key = (id(self.tokenizer), self._manual_special_tokens_required, self._manual_cls_token_id,
+               self._manual_sep_token_id)
+        cached = getattr(self, "_pack_template_cache", None)
+        if cached is None or cached[0] != key:
+            template = host_pack.special_token_template(
+                self.tokenizer, self._manual_special_tokens_required, self._manual_cls_token_id,
+                self._manual_sep_token_id)
+            cached = self._pack_template_cache = (key, template)
+        return cached[1]
+
+    def _pack_native(self, plans: list[_ContextPlan], query_tokens: list[list[int]], sep_len: int,
+                     max_fragment_tokens: int, strip: bool, respect: bool) -> BlockTable | None:
+        """Fragment windows -> filter -> blocks -> table in one ``opv_pack_build`` call (csrc/host_pack.cu).
+
+        Returns None for the inputs the native packer leaves to the Python restatement below: a tokenizer whose
+        ``build_inputs_with_special_tokens`` is not ``head + q + mid + ctx + tail``, and contexts whose sentences
+        all tokenise to nothing (the reference's whole-context fallback fragment, standalone:813-816)."""
+        if getattr(self, "host_pack_mode", "native") != "native" or not plans:
+            return None
+        template = self._pack_template()
+        if template is None or any(not any(p.token_lists) for p in plans):
+            return None
+        packed = host_pack.pack_blocks(
+            self.tokenizer, [t for p in plans for t in p.token_lists], [len(p.token_lists) for p in plans],
+            [p.query_idx for p in plans], [len(p.prefix_sentences) for p in plans], query_tokens,
+            template=template, max_length=self.max_length, max_fragment_tokens=max_fragment_tokens,
+            keep_sentence_boundaries=respect, sep_len=sep_len, strip_sentences=strip)
+        for c, p in enumerate(plans):
+            b0, b1 = int(packed.ctx_block_offsets[c]), int(packed.ctx_block_offsets[c + 1])
+            p.block_slots = list(range(b0, b1))
+            p.sentence_base = int(packed.ctx_sentence_base[c])
+            p.n_blocks = b1 - b0
+            p.n_fragments = max(1, p.n_blocks)
+        return packed.table
 
     # ------------------------------------------------------------------ process()
     def process(
@@ -833,9 +874,13 @@ class OpenProvenceModel:
             t_local = {k: 0.0 for k in timing}
             plans_k, _ = self._plan_contexts(queries, contexts, titles, splitter, strip_sentences, t_local,
                                              pairs=pairs_k, query_tokens=query_tokens)
-            self._fragmentize(plans_k, max_fragment_tokens, strip_sentences, respect_sentence_boundaries, t_local)
             t0 = perf_counter()
-            table_k = self._build_table(plans_k, query_tokens, sep_len)
+            table_k = self._pack_native(plans_k, query_tokens, sep_len, max_fragment_tokens, strip_sentences,
+                                        respect_sentence_boundaries)
+            if table_k is None:
+                self._fragmentize(plans_k, max_fragment_tokens, strip_sentences, respect_sentence_boundaries, t_local)
+                t0 = perf_counter()
+                table_k = self._build_table(plans_k, query_tokens, sep_len)
             return plans_k, table_k, t_local, perf_counter() - t0
 
         if hasattr(self._scorer, "max_tokens"):
@@ -904,7 +949,7 @@ class OpenProvenceModel:
                 fallback_title: Any = None
                 if first_line_as_title and prefix:
                     fallback_title = prefix[0] if len(prefix) == 1 else list(prefix)
-                if p is None or not p.fragments:
+                if p is None or not p.n_fragments:
                     q["pruned"].append(entry)
                     q["score"].append(None)
                     q["compression"].append(0.0)
@@ -913,7 +958,7 @@ class OpenProvenceModel:
                     q["title"].append(fallback_title)
                     q["probs"].append([])
                     continue
-                if not p.blocks:
+                if not p.n_blocks:
                     q["pruned"].append(entry)
                     q["score"].append(None)
                     q["compression"].append(0.0)

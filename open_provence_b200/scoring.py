@@ -24,6 +24,9 @@ class BlockTable:
     frag_local: list[tuple[int, int]] = field(default_factory=list)  # block-local [start, end)
     sent_offsets: list[int] = field(default_factory=lambda: [0])  # CSR over sentences
     sent_frag_index: list[int] = field(default_factory=list)  # fragment slots of each sentence
+    # set by the native packer (host_pack.pack_blocks): all blocks in one array, block_ids are views into it
+    packed_ids: np.ndarray | None = None
+    block_offsets: np.ndarray | None = None
 
     @property
     def n_blocks(self) -> int:
@@ -109,7 +112,11 @@ class DeviceScorer:
             chunk = blocks[lo:hi]
             cu = np.zeros(len(chunk) + 1, dtype=np.int32)
             np.cumsum([lengths[b] for b in chunk], out=cu[1:])
-            ids = np.concatenate([table.block_ids[b] for b in chunk]).astype(np.int32, copy=False)
+            if table.packed_ids is not None and int(chunk[-1]) - int(chunk[0]) + 1 == len(chunk) and np.all(np.diff(chunk) == 1):
+                # natively packed table, consecutive blocks: the launch input is a slice of the packed array
+                ids = table.packed_ids[int(table.block_offsets[chunk[0]]) : int(table.block_offsets[chunk[-1] + 1])]
+            else:
+                ids = np.concatenate([table.block_ids[b] for b in chunk]).astype(np.int32, copy=False)
             counts = [int(first_slot[b + 1] - first_slot[b]) for b in chunk]
             slots = np.concatenate([order[first_slot[b] : first_slot[b + 1]] for b in chunk]) if n_frags else np.zeros(0, np.int64)
             base = np.repeat(cu[:-1].astype(np.int64), counts)

@@ -65,7 +65,7 @@ class _CpuRecordedScorer:
         fm = frag_mean.numpy()
         prob, keep = [], []
         for s in range(table.n_sentences):
-            members = table.sent_frag_index[table.sent_offsets[s] : table.sent_offsets[s + 1]]
+            members = list(table.sent_frag_index[table.sent_offsets[s] : table.sent_offsets[s + 1]])
             p = max(0.0, min(float(np.mean([float(fm[k]) for k in members])) if members else 0.0, 1.0))
             prob.append(p)
             keep.append(p > threshold)
