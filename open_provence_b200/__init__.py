@@ -6,11 +6,14 @@ Only what the hot path needs lives here:
   engine.py    weight packing + launches
   modeling.py  drop-in ``OpenProvenceModel`` (from_pretrained / forward / process)
   encoder.py   drop-in ``OpenProvenceEncoder`` inference APIs (token-level pruning, chunk votes)
+  host_pack.py native block assembly between tokenizer and device (opv_pack_*)
+  hf_auto.py   ``AutoModel`` / ``auto_map`` entry points of the reference, resolved to this engine
 """
 
 __version__ = "0.1.0"
 
-__all__ = ["__version__", "OpenProvenceModel", "OpenProvenceEncoder", "OpenProvenceConfig"]
+__all__ = ["__version__", "OpenProvenceModel", "OpenProvenceEncoder", "OpenProvenceConfig",
+           "OpenProvenceForSequenceClassification", "OpenProvenceForTokenClassification", "register_auto_classes"]
 
 
 def __getattr__(name):  # lazy: importing the package must not pull torch / the shared library in
@@ -26,4 +29,10 @@ def __getattr__(name):  # lazy: importing the package must not pull torch / the 
         from .config import OpenProvenceConfig
 
         return OpenProvenceConfig
+    if name in ("OpenProvenceForSequenceClassification", "OpenProvenceForTokenClassification",
+                "OpenProvenceEncoderForSequenceClassification", "OpenProvenceEncoderForTokenClassification",
+                "register_auto_classes"):
+        from . import hf_auto
+
+        return getattr(hf_auto, name)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -198,6 +198,9 @@ class OpenProvenceEncoder:
         cfg = self.config.to_dict()
         cfg["max_length"] = int(self.max_length)
         cfg["mode"] = "reranking_pruning"
+        from .hf_auto import with_auto_map
+
+        cfg = with_auto_map(cfg)  # encoder.py:1078-1085: the reference's Auto* entry points
         (out / "config.json").write_text(json.dumps(cfg, indent=2, ensure_ascii=False, default=str))
         if self.tokenizer is not None:
             self.tokenizer.save_pretrained(str(out))
