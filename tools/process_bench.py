@@ -2,7 +2,7 @@
 """End-to-end ``OpenProvenceModel.process()`` on the GPU: text in, pruned text out (base-130M dims, random
 weights, the tiny golden tokenizer).  Prints the stage timings the reference reports (result["timing"]).
 
-    python tools/process_bench.py [n_contexts] [max_length] [model]
+    python tools/process_bench.py [n_contexts] [max_length] [model] [native|python]
 """
 import sys, time
 from pathlib import Path
@@ -30,6 +30,7 @@ def main():
     config.max_length = max_length
     model = OpenProvenceModel(config, syn.random_state_dict(config.base_model_config, seed=0), tok, device="cuda", dtype="bf16")
     model.max_length = max_length
+    model.host_pack_mode = sys.argv[4] if len(sys.argv) > 4 else "native"  # block assembly: C++ (default) or Python
     rng = np.random.default_rng(0)
     words = ["alpha", "beta", "gamma", "delta", "pruning", "context", "question", "answer", "tokyo", "river"]
     def sentence():
@@ -42,7 +43,7 @@ def main():
     t0 = time.perf_counter()
     out = model.process(**kw)
     dt = time.perf_counter() - t0
-    print(f"{name}: {n_ctx} contexts, max_length {max_length}: {dt * 1e3:.1f} ms -> {n_ctx / dt:.0f} contexts/s end to end")
+    print(f"{name} [{model.host_pack_mode} pack]: {n_ctx} contexts, max_length {max_length}: {dt * 1e3:.1f} ms -> {n_ctx / dt:.0f} contexts/s end to end")
     print({k: round(v, 4) for k, v in out["timing"].items()})
     kept = sum(len(p) for p in out["pruned_context"])
     print(f"pruned characters kept: {kept} of {sum(len(c) for c in contexts)}")
