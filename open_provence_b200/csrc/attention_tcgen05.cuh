@@ -135,6 +135,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // the prologue above overlapped the previous kernel; qkv is visible from here on
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for ptxas: a per-thread TMEM address makes every tcgen05.mma an ELECT / R2UR.BROADCAST waterfall loop
 
   if (warp >= 4) {

@@ -106,6 +106,8 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // the prologue above overlapped the previous kernel; qkv is visible from here on
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform (single UTCHMMA per MMA)
 
   if (warp == 8) {

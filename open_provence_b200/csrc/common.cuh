@@ -148,6 +148,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Programmatic dependent launch (PDL).  A kernel launched with programmaticStreamSerializationAllowed may become
+// resident while its predecessor in the stream is still running; pdl_wait() blocks until every prerequisite grid has
+// completed and its memory is visible, so everything before it (barrier init, TMEM allocation, descriptor prefetch)
+// overlaps the predecessor's tail.  pdl_launch_dependents() lets the NEXT kernel in the stream do the same with this
+// one.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

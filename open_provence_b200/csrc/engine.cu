@@ -105,6 +105,33 @@ int g_gemm_pair = 1;
 // ROPE GEMM: 1 = a cluster finishes all column tiles of a row block before the next row block (cos|sin staged once)
 int g_gemm_group_rows = 1;
 
+// 1 = the kernels that call pdl_wait() (GEMMs, attention, LayerNorm family) are launched with programmatic stream
+// serialization, so each one's prologue overlaps its predecessor's tail; 0 = plain stream order
+int g_pdl = 1;
+// Measured on B200 (profiles/r1t_pdl.md): PDL takes 18-23 % off a 481-token forward, 12 % off a 2048-token one and 1.5 %
+// off 32768 tokens, but costs 1.4 % at 65536 and 0.9 % at 131072 tokens (dependents parked on the SMs while 200-us
+// kernels run), so it is applied to forwards of at most this many tokens.
+long long g_pdl_max_tokens = 32768;
+thread_local long long t_forward_tokens = 0;  // tokens of the forward being enqueued (0 outside opv_forward_packed)
+
+// Launch through cudaLaunchKernelEx so that the PDL attribute can ride along.  Only for kernels that call
+// opv::pdl_wait() before their first global-memory access.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (g_pdl && t_forward_tokens <= g_pdl_max_tokens) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <int BLOCK_N, int EPI>
 int set_gemm_attr() {
   OPV_CUDA(cudaFuncSetAttribute(opv::gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>,
@@ -155,9 +182,8 @@ int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUten
                    const opv::GemmEpilogueArgs& ep, int64_t M, int N, int K, cudaStream_t stream) {
   const int64_t tiles = ((M + opv::kGemmBlockM - 1) / opv::kGemmBlockM) * (N / BLOCK_N);
   const int grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
-  opv::gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>
-      <<<grid, opv::gemm_threads(EPI), opv::GemmSmemLayout<BLOCK_N, EPI>::kTotal, stream>>>(tm_a, tm_b, tm_c, ep, (int)M, N,
-                                                                                       K);
+  launch_pdl(opv::gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>, dim3(grid), dim3(opv::gemm_threads(EPI)),
+             opv::GemmSmemLayout<BLOCK_N, EPI>::kTotal, stream, tm_a, tm_b, tm_c, ep, (int)M, N, K);
   OPV_LAUNCH_CHECK("gemm_bf16_tcgen05_kernel");
   return OPV_OK;
 }
@@ -171,9 +197,8 @@ int launch_gemm_pair(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUt
   const int clusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
   opv::GemmEpilogueArgs ep_launch = ep;
   ep_launch.group_rows = (EPI == opv::kEpiRope && g_gemm_group_rows && pairs_m >= 4 * clusters) ? 1 : 0;
-  opv::gemm_bf16_tcgen05_pair_kernel<EPI>
-      <<<2 * clusters, opv::gemm_threads(EPI), opv::GemmPairSmemLayout<EPI>::kTotal, stream>>>(tm_a, tm_b, tm_c, ep_launch,
-                                                                                          (int)M, N, K);
+  launch_pdl(opv::gemm_bf16_tcgen05_pair_kernel<EPI>, dim3(2 * clusters), dim3(opv::gemm_threads(EPI)),
+             opv::GemmPairSmemLayout<EPI>::kTotal, stream, tm_a, tm_b, tm_c, ep_launch, (int)M, N, K);
   OPV_LAUNCH_CHECK("gemm_bf16_tcgen05_pair_kernel");
   return OPV_OK;
 }
@@ -255,7 +280,8 @@ inline unsigned row_grid(int64_t M) { return static_cast<unsigned>((M + opv::kRo
 template <typename OutT>
 int launch_layernorm(const float* h, const float* w, OutT* x, int64_t M, int H, float eps, cudaStream_t s) {
   if (M <= 0) return OPV_OK;
-  OPV_DISPATCH_VEC(H, opv::layernorm_kernel<OutT, VEC><<<row_grid(M), opv::kRowWarps * 32, 0, s>>>(h, w, x, M, eps));
+  OPV_DISPATCH_VEC(H, launch_pdl(opv::layernorm_kernel<OutT, VEC>, dim3(row_grid(M)), dim3(opv::kRowWarps * 32), 0, s, h,
+                                 w, x, M, eps));
   OPV_LAUNCH_CHECK("layernorm_kernel");
   return OPV_OK;
 }
@@ -264,8 +290,8 @@ template <typename EmbT, typename OutT>
 int launch_embed_ln(const int32_t* ids, const EmbT* emb, const float* w, float* h, OutT* x, int64_t M, int H, int V,
                     float eps, cudaStream_t s) {
   if (M <= 0) return OPV_OK;
-  OPV_DISPATCH_VEC(H, opv::embed_ln_kernel<EmbT, OutT, VEC>
-                       <<<row_grid(M), opv::kRowWarps * 32, 0, s>>>(ids, emb, w, h, x, M, V, eps));
+  OPV_DISPATCH_VEC(H, launch_pdl(opv::embed_ln_kernel<EmbT, OutT, VEC>, dim3(row_grid(M)), dim3(opv::kRowWarps * 32), 0,
+                                 s, ids, emb, w, h, x, M, V, eps));
   OPV_LAUNCH_CHECK("embed_ln_kernel");
   return OPV_OK;
 }
@@ -273,8 +299,8 @@ int launch_embed_ln(const int32_t* ids, const EmbT* emb, const float* w, float* 
 int launch_final_prune(const float* h, const float* w, const float* wp, const float* bp, float* logits, int64_t M,
                        int H, float eps, cudaStream_t s) {
   if (M <= 0) return OPV_OK;
-  OPV_DISPATCH_VEC(H, opv::final_ln_prune_kernel<VEC>
-                       <<<row_grid(M), opv::kRowWarps * 32, 0, s>>>(h, w, wp, bp, logits, M, eps));
+  OPV_DISPATCH_VEC(H, launch_pdl(opv::final_ln_prune_kernel<VEC>, dim3(row_grid(M)), dim3(opv::kRowWarps * 32), 0, s, h,
+                                 w, wp, bp, logits, M, eps));
   OPV_LAUNCH_CHECK("final_ln_prune_kernel");
   return OPV_OK;
 }
@@ -295,14 +321,16 @@ int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, i
     // default (1): one softmax thread per row for global layers (649 vs 585 TFLOP/s at S = 2048), two threads per row
     // for sliding-window layers (0.156 vs 0.176 ms per layer at 64 x 2048); 3 / 4 force one of them everywhere
     if (g_attention_impl == 3 || (g_attention_impl == 1 && half_window >= 0))
-      opv::attention_tcgen05_v3_kernel<<<grid, opv::kFa3Threads, opv::Fa3SmemLayout::kTotal, s>>>(
-          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq);
+      launch_pdl(opv::attention_tcgen05_v3_kernel, dim3(grid), dim3(opv::kFa3Threads), opv::Fa3SmemLayout::kTotal, s,
+                 *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq);
     else if (g_attention_impl == 1 || g_attention_impl == 4)
-      opv::attention_tcgen05_kernel<true><<<grid, opv::kFaThreads, opv::FaSmemLayout<true>::kTotal, s>>>(
-          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq, g_attention_trace);
+      launch_pdl(opv::attention_tcgen05_kernel<true>, dim3(grid), dim3(opv::kFaThreads), opv::FaSmemLayout<true>::kTotal,
+                 s, *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq,
+                 g_attention_trace);
     else
-      opv::attention_tcgen05_kernel<false><<<grid, opv::kFaThreads, opv::FaSmemLayout<false>::kTotal, s>>>(
-          *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq, g_attention_trace);
+      launch_pdl(opv::attention_tcgen05_kernel<false>, dim3(grid), dim3(opv::kFaThreads),
+                 opv::FaSmemLayout<false>::kTotal, s, *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window,
+                 n_seqs, tiles_per_seq, g_attention_trace);
     OPV_LAUNCH_CHECK("attention_tcgen05_kernel");
   } else if (dtype == OPV_DTYPE_BF16) {
     dim3 grid((max_seqlen + opv::kAttBlockM - 1) / opv::kAttBlockM, heads, n_seqs);
@@ -509,6 +537,10 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
   int32_t* pos = reinterpret_cast<int32_t*>(ws + wl.pos);
   const int half_window = c.local_window / 2;
   int rc = OPV_OK;
+  struct ForwardTokens {  // launch_pdl() decides per forward whether the PDL attribute pays (g_pdl_max_tokens)
+    explicit ForwardTokens(long long t) { t_forward_tokens = t; }
+    ~ForwardTokens() { t_forward_tokens = 0; }
+  } forward_tokens(T);
 
   {
     LaunchScope sc(e, stream, OPV_PROF_MISC);
@@ -823,6 +855,14 @@ int opv_set_option(const char* name, int64_t value) {
   }
   if (strcmp(name, "gemm_group_rows") == 0) {
     g_gemm_group_rows = value != 0;
+    return OPV_OK;
+  }
+  if (strcmp(name, "pdl") == 0) {
+    g_pdl = value != 0;
+    return OPV_OK;
+  }
+  if (strcmp(name, "pdl_max_tokens") == 0) {
+    g_pdl_max_tokens = value;
     return OPV_OK;
   }
   if (strcmp(name, "gemm_pair") == 0) {

@@ -250,6 +250,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // the prologue above overlapped the previous kernel; its outputs are visible from here on
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for ptxas: a per-thread TMEM address makes every tcgen05.mma an ELECT / R2UR.BROADCAST waterfall loop
 
   if (warp == 0) {
@@ -432,6 +434,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
   tc_fence_before();
   cluster_sync_all();  // barrier inits of both CTAs visible before any remote arrive / multicast commit
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // the prologue above overlapped the previous kernel; its outputs are visible from here on
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for ptxas: a per-thread TMEM address makes every tcgen05.mma an ELECT / R2UR.BROADCAST waterfall loop
 
   if (warp == 0) {

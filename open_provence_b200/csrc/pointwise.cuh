@@ -72,6 +72,8 @@ template <typename EmbT, typename OutT, int VEC>
 __global__ void __launch_bounds__(kRowWarps * 32)
 embed_ln_kernel(const int32_t* __restrict__ ids, const EmbT* __restrict__ emb, const float* __restrict__ w,
                 float* __restrict__ h, OutT* __restrict__ x, const int64_t M, const int vocab, const float eps) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel in the stream
   constexpr int H = VEC * 128;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
@@ -99,6 +101,8 @@ template <typename OutT, int VEC>
 __global__ void __launch_bounds__(kRowWarps * 32)
 layernorm_kernel(const float* __restrict__ h, const float* __restrict__ w, OutT* __restrict__ x, const int64_t M,
                  const float eps) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel in the stream
   constexpr int H = VEC * 128;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
@@ -118,6 +122,8 @@ template <int VEC>
 __global__ void __launch_bounds__(kRowWarps * 32)
 final_ln_prune_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ wp,
                       const float* __restrict__ bp, float* __restrict__ logits, const int64_t M, const float eps) {
+  pdl_launch_dependents();
+  pdl_wait();  // inputs come from the previous kernel in the stream
   constexpr int H = VEC * 128;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
