@@ -122,7 +122,11 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
  * 0 = mma.sync flash kernel (v1), 1 = tcgen05 (default: one softmax thread per query row for global layers, two
  * per row for sliding-window layers), 2 = one thread per row with P staged through shared memory, 3 = two
  * threads per row everywhere, 4 = one thread per row everywhere.  "attention_trace_ptr": device buffer for the clock64() timeline of
- * tools/attn_check.py (0 = off, the product setting). */
+ * tools/attn_check.py (0 = off, the product setting).  "gemm_pair": 1 = CTA-pair (cta_group::2) GEMM for 256-wide
+ * tiles (default), 0 = single-CTA kernel.  "gemm_group_rows": row-grouped tile order of the RoPE GEMM (default 1).
+ * "pdl": 1 = GEMM / attention / LayerNorm kernels are launched with programmatic stream serialization so that each
+ * kernel's prologue overlaps its predecessor's tail (default), 0 = plain stream order; "pdl_max_tokens": forwards
+ * with more packed tokens than this are launched without it (default 32768, profiles/r1t_pdl.md). */
 int opv_set_option(const char* name, int64_t value);
 
 /* Per-kernel-class timing of the forward, measured with CUDA events on the launch stream.

@@ -129,3 +129,22 @@ def test_ragged_batch_equals_single_sequences_at_base_dims():
         torch.cuda.synchronize()
         assert torch.equal(prune_all[lo:hi], prune_one), f"sequence {b} (len {n}) differs inside the batch"
         assert torch.equal(rank_all[b : b + 1], rank_one)
+
+
+@pytest.mark.parametrize("name", ["xsmall-30M", "base-130M"])
+def test_programmatic_dependent_launch_is_bit_identical(name):
+    """The PDL attribute only moves kernel prologues ahead of the predecessor's tail (``griddepcontrol.wait`` comes
+    before the first global access): outputs with it, without it, and past the token threshold are the same bits."""
+    from open_provence_b200 import ops
+
+    cfg, sd, seqs = _case(name)
+    outs = []
+    for option, value in (("pdl", 1), ("pdl", 0), ("pdl_max_tokens", 0)):
+        ops.set_option(option, value)
+        try:
+            outs.append(_run(cfg, sd, seqs, "bf16"))
+        finally:
+            ops.set_option("pdl", 1)
+            ops.set_option("pdl_max_tokens", 32768)
+    for prune, rank in outs[1:]:
+        assert np.array_equal(prune, outs[0][0]) and np.array_equal(rank, outs[0][1])
