@@ -84,8 +84,129 @@ class DeviceScorer:
     def run(self, table: BlockTable, threshold: float) -> dict[str, np.ndarray]:
         """Single-GPU path: score every block, then prune."""
         self.last_n_blocks = table.n_blocks
+        if self.single_launch_fast_path:
+            out = self._run_single_launch(table, threshold)
+            if out is not None:
+                return out
         rank_score, frag_mean_dev, kept = self.score_blocks(table, np.arange(table.n_blocks))
         return self.prune(table, rank_score, frag_mean_dev, kept, threshold)
+
+    # ------------------------------------------------------------------ one launch, one copy each way
+    single_launch_fast_path = True
+
+    def _staging(self, n_in: int, n_out: int):
+        """Pinned host + device staging buffers (int32 inputs, byte outputs), grown on demand and reused: the call
+        synchronises before it returns, so nothing is in flight when the next call overwrites them."""
+        dev = self.engine.device
+        st = getattr(self, "_stage", None)
+        if st is None or st["h_in"].numel() < n_in or st["h_out"].numel() < n_out:
+            cap_in = max(n_in, 2 * (st["h_in"].numel() if st else 0), 1 << 16)
+            cap_out = max(n_out, 2 * (st["h_out"].numel() if st else 0), 1 << 14)
+            st = self._stage = {
+                "h_in": torch.empty(cap_in, dtype=torch.int32).pin_memory(),
+                "d_in": torch.empty(cap_in, dtype=torch.int32, device=dev),
+                "h_out": torch.empty(cap_out, dtype=torch.uint8).pin_memory(),
+                "d_out": torch.empty(cap_out, dtype=torch.uint8, device=dev),
+            }
+        return st
+
+    def _run_single_launch(self, table: BlockTable, threshold: float) -> dict[str, np.ndarray] | None:
+        """The whole table in ONE forward launch with ONE host->device and ONE device->host copy (the general
+        path makes six small copies each way, which is a fifth of the latency of a single-pair call).  Same
+        kernels and same arithmetic as score_blocks() + prune(); returns None when the table needs several
+        launches or has no fragments / sentences."""
+        from . import _native as N
+
+        n_blocks, n_sent = table.n_blocks, table.n_sentences
+        frag_block = np.asarray(table.frag_block, dtype=np.int64)
+        n_frags = int(frag_block.shape[0])
+        if n_blocks == 0 or n_blocks > 65535 or n_frags == 0 or n_sent == 0:
+            return None
+        if table.block_offsets is not None:
+            cu64 = np.asarray(table.block_offsets, dtype=np.int64)
+        else:
+            cu64 = np.zeros(n_blocks + 1, dtype=np.int64)
+            np.cumsum([int(b.shape[0]) for b in table.block_ids], out=cu64[1:])
+        n_tokens = int(cu64[-1])
+        if n_tokens == 0 or n_tokens > self.max_tokens:
+            return None
+        eng = self.engine
+        dev = eng.device
+        frag_local = np.asarray(table.frag_local, dtype=np.int64).reshape(-1, 2)
+        ranges = (frag_local + cu64[:-1][frag_block][:, None]).astype(np.int32)
+        sent_index = np.asarray(table.sent_frag_index, dtype=np.int32)
+        sent_offsets = np.asarray(table.sent_offsets, dtype=np.int32)
+        max_seqlen = int(np.diff(cu64).max())
+
+        def up4(n: int) -> int:
+            return (n + 3) & ~3
+
+        o_ids = 0
+        o_cu = o_ids + up4(n_tokens)
+        o_rng = o_cu + up4(n_blocks + 1)
+        o_off = o_rng + up4(2 * n_frags)
+        o_idx = o_off + up4(n_sent + 1)
+        n_in = o_idx + up4(max(int(sent_index.shape[0]), 1))
+        b_prob = 0
+        b_score = b_prob + 8 * n_sent
+        b_mean = b_score + 4 * up4(n_blocks)
+        b_keep = b_mean + 4 * up4(n_frags)
+        b_near = b_keep + up4(n_sent)
+        n_out = b_near + up4(n_sent)
+        st = self._staging(n_in, n_out)
+        h_in = st["h_in"].numpy()
+        if table.packed_ids is not None:
+            h_in[o_ids : o_ids + n_tokens] = table.packed_ids
+        else:
+            np.concatenate(table.block_ids, out=h_in[o_ids : o_ids + n_tokens])
+        h_in[o_cu : o_cu + n_blocks + 1] = cu64
+        h_in[o_rng : o_rng + 2 * n_frags] = ranges.reshape(-1)
+        h_in[o_off : o_off + n_sent + 1] = sent_offsets
+        h_in[o_idx : o_idx + sent_index.shape[0]] = sent_index
+        d_in, d_out = st["d_in"], st["d_out"]
+        d_in[:n_in].copy_(st["h_in"][:n_in], non_blocking=True)
+        prune, rank = eng.forward_packed(d_in[o_ids : o_ids + n_tokens], d_in[o_cu : o_cu + n_blocks + 1], max_seqlen)
+        p_in, p_out, stream = d_in.data_ptr(), d_out.data_ptr(), eng._stream()
+        with torch.cuda.device(dev):
+            N.check(eng.lib.opv_fragment_means(
+                prune.data_ptr(), n_tokens, p_in + 4 * o_rng, n_frags, p_out + b_mean, rank.data_ptr(), n_blocks,
+                int(rank.shape[1]), p_out + b_score, stream), "opv_fragment_means")
+            N.check(eng.lib.opv_sentence_prune(
+                p_out + b_mean, p_in + 4 * o_off, p_in + 4 * o_idx, n_sent, float(threshold), float(self.guard),
+                p_out + b_prob, p_out + b_keep, p_out + b_near, stream), "opv_sentence_prune")
+        st["h_out"][:n_out].copy_(d_out[:n_out], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        h_out = st["h_out"].numpy()
+        prob_h = h_out[b_prob : b_prob + 8 * n_sent].view(np.float64).copy()
+        rank_score = h_out[b_score : b_score + 4 * n_blocks].view(np.float32).copy()
+        frag_mean_h = h_out[b_mean : b_mean + 4 * n_frags].view(np.float32).copy()
+        keep_h = h_out[b_keep : b_keep + n_sent].astype(bool)
+        near_h = h_out[b_near : b_near + n_sent].astype(bool)
+        if near_h.any():  # rare: re-evaluate with the reference's exact CPU arithmetic (same as prune())
+            self._reevaluate_near(near_h, sent_index, sent_offsets, [(ranges, np.arange(n_frags), prune)], frag_mean_h,
+                                  prob_h, keep_h, threshold)
+        return {"rank_score": rank_score, "frag_mean": frag_mean_h, "sent_prob": prob_h, "keep": keep_h, "near": near_h}
+
+    @staticmethod
+    def _reevaluate_near(near_h, sent_index, sent_offsets, kept_logits, frag_mean_h, prob_h, keep_h, threshold) -> None:
+        """Sentences within the guard band of the threshold: recompute from the fp32 logits exactly as the
+        reference does on the CPU (standalone:2918-2920, 3081, 3118-3119); updates prob_h / keep_h in place."""
+        needed = set()
+        for s in np.nonzero(near_h)[0]:
+            needed.update(int(k) for k in sent_index[sent_offsets[s] : sent_offsets[s + 1]])
+        slot_mean: dict[int, float] = {}
+        for ranges, slots, prune in kept_logits:
+            for j, slot in enumerate(slots):
+                if int(slot) in needed:
+                    a, b = int(ranges[j, 0]), int(ranges[j, 1])
+                    logits = prune[a:b].cpu().numpy() if b > a else np.zeros((0, 2), np.float32)
+                    slot_mean[int(slot)] = exact_fragment_mean(logits)
+        for s in np.nonzero(near_h)[0]:
+            members = [int(k) for k in sent_index[sent_offsets[s] : sent_offsets[s + 1]]]
+            # fragments scored on another rank have no local logits: keep their device mean
+            exact = exact_sentence_probability([slot_mean.get(k, float(frag_mean_h[k])) for k in members])
+            prob_h[s] = exact
+            keep_h[s] = exact > threshold
 
     def score_blocks(self, table: BlockTable, blocks: np.ndarray):
         """Forward + score conversion + fragment means for ``blocks`` (indices into the table).
@@ -155,20 +276,5 @@ class DeviceScorer:
         frag_mean_h = frag_mean_dev[:n_frags].cpu().numpy() if n_frags else np.zeros(0, np.float32)
 
         if near_h.any():  # rare: re-evaluate with the reference's exact CPU arithmetic
-            needed = set()
-            for s in np.nonzero(near_h)[0]:
-                needed.update(int(k) for k in sent_index[sent_offsets[s] : sent_offsets[s + 1]])
-            slot_mean: dict[int, float] = {}
-            for ranges, slots, prune in kept_logits:
-                for j, slot in enumerate(slots):
-                    if int(slot) in needed:
-                        a, b = int(ranges[j, 0]), int(ranges[j, 1])
-                        logits = prune[a:b].cpu().numpy() if b > a else np.zeros((0, 2), np.float32)
-                        slot_mean[int(slot)] = exact_fragment_mean(logits)
-            for s in np.nonzero(near_h)[0]:
-                members = [int(k) for k in sent_index[sent_offsets[s] : sent_offsets[s + 1]]]
-                # fragments scored on another rank have no local logits: keep their device mean
-                exact = exact_sentence_probability([slot_mean.get(k, float(frag_mean_h[k])) for k in members])
-                prob_h[s] = exact
-                keep_h[s] = exact > threshold
+            self._reevaluate_near(near_h, sent_index, sent_offsets, kept_logits, frag_mean_h, prob_h, keep_h, threshold)
         return {"rank_score": rank_score, "frag_mean": frag_mean_h, "sent_prob": prob_h, "keep": keep_h, "near": near_h}

@@ -214,3 +214,43 @@ def test_raw_predictions_and_thresholds_on_the_engine(model_fp32, tiny_ckpt_dir)
             assert {str(k): v for k, v in got["predictions"].items()} == want["predictions"]
     finally:
         model_fp32.max_length = saved
+
+
+@pytest.mark.parametrize("which", ["fp32", "bf16"])
+def test_single_launch_fast_path_equals_general_path(which, model_fp32, model_bf16):
+    """One staged copy each way (DeviceScorer._run_single_launch) against the per-array copies of
+    score_blocks() + prune(): same kernels on the same inputs, so every output is the same bits."""
+    eng = (model_fp32 if which == "fp32" else model_bf16).engine
+    rng = np.random.default_rng(9)
+    table = BlockTable()
+    for b in range(7):
+        n = int(rng.integers(20, 300))
+        ids = rng.integers(5, 260, size=n).astype(np.int32)
+        ids[0] = 1
+        table.block_ids.append(ids)
+        at = 2
+        while at < n - 1:
+            end = min(n - 1, at + int(rng.integers(1, 40)))
+            table.frag_block.append(b)
+            table.frag_local.append((at, end if rng.random() > 0.1 else at))  # some empty ranges (mean := 1.0)
+            if rng.random() < 0.7 or not table.sent_frag_index:
+                table.sent_frag_index.append(len(table.frag_block) - 1)
+                table.sent_offsets.append(len(table.sent_frag_index))
+            else:  # fragment joins the previous sentence
+                table.sent_frag_index.append(len(table.frag_block) - 1)
+                table.sent_offsets[-1] = len(table.sent_frag_index)
+            at = end
+        table.sent_offsets.append(len(table.sent_frag_index))  # a sentence without fragments (probability 0)
+    scorer = DeviceScorer(eng)
+    fast = scorer.run(table, 0.3)
+    assert getattr(scorer, "_stage", None) is not None, "the fast path did not run"
+    scorer.single_launch_fast_path = False
+    slow = scorer.run(table, 0.3)
+    for key in ("rank_score", "frag_mean", "sent_prob", "keep", "near"):
+        assert np.array_equal(fast[key], slow[key]), key
+    # a table too large for one launch falls back to the general path
+    scorer.single_launch_fast_path = True
+    scorer.max_tokens = 256
+    assert scorer._run_single_launch(table, 0.3) is None
+    again = scorer.run(table, 0.3)
+    assert np.array_equal(again["keep"], slow["keep"]) and np.allclose(again["sent_prob"], slow["sent_prob"], atol=1e-12)
