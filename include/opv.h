@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define OPV_ABI_VERSION 1
+#define OPV_ABI_VERSION 2
 #define OPV_MAX_LAYERS 64
 
 typedef enum opv_status {
@@ -63,6 +63,7 @@ typedef struct opv_config {
   float norm_eps;               /* 1e-5 */
   int32_t dtype;                /* opv_dtype */
   int32_t fuse_epilogues;       /* bf16 only: 1 = RoPE/GeGLU/residual fused into the GEMM epilogues */
+  int32_t classifier_pooling;   /* ranking head input (HF:621-630): 0 = "cls" (first token), 1 = "mean" over the tokens */
   uint8_t layer_is_global[OPV_MAX_LAYERS]; /* 1 = full attention, 0 = sliding window */
 } opv_config;
 

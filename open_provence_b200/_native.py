@@ -10,7 +10,7 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libopv_sm100.so"
 
-OPV_ABI_VERSION = 1
+OPV_ABI_VERSION = 2
 OPV_MAX_LAYERS = 64
 OPV_DTYPE_BF16 = 0
 OPV_DTYPE_F32 = 1
@@ -41,6 +41,7 @@ class OpvConfig(C.Structure):
         ("norm_eps", C.c_float),
         ("dtype", C.c_int32),
         ("fuse_epilogues", C.c_int32),
+        ("classifier_pooling", C.c_int32),
         ("layer_is_global", C.c_uint8 * OPV_MAX_LAYERS),
     ]
 

@@ -394,7 +394,7 @@ struct LaunchScope {
 };
 
 struct WorkspaceLayout {
-  size_t h, x, qkv, attn, act, u, pos, cls, y, total;
+  size_t h, x, qkv, attn, act, u, pos, cls, y, pool, total;
 };
 
 static WorkspaceLayout workspace_layout(const opv_engine* e, int64_t T, int64_t n_seqs) {
@@ -418,6 +418,8 @@ static WorkspaceLayout workspace_layout(const opv_engine* e, int64_t T, int64_t 
   const size_t seqs = static_cast<size_t>(n_seqs > 0 ? n_seqs : 1);
   l.cls = take(seqs * H * 4);  // rank head: LN(CLS row)
   l.y = take(seqs * H * 4);    // rank head: gelu(dense(cls))
+  // mean pooling: per-chunk sums of the final-normed rows (slot = begin / chunk + s + c, pointwise.cuh)
+  l.pool = take(e->cfg.classifier_pooling ? (rows / opv::kPoolChunkRows + seqs + 2) * H * 4 : 0);
   l.total = off;
   return l;
 }
@@ -445,6 +447,9 @@ int opv_create(const opv_config* cfg, const opv_weights* w, int device, opv_hand
   if (cfg->intermediate_size % 128 != 0)
     return fail(OPV_ERR_UNSUPPORTED, "intermediate_size %d must be a multiple of 128", cfg->intermediate_size);
   if (cfg->num_labels < 1) return fail(OPV_ERR_INVALID_ARGUMENT, "num_labels must be >= 1");
+  if (cfg->classifier_pooling != 0 && cfg->classifier_pooling != 1)
+    return fail(OPV_ERR_INVALID_ARGUMENT, "classifier_pooling must be 0 (cls) or 1 (mean), got %d",
+                cfg->classifier_pooling);
   if (cfg->dtype != OPV_DTYPE_BF16 && cfg->dtype != OPV_DTYPE_F32)
     return fail(OPV_ERR_INVALID_ARGUMENT, "unknown dtype %d", cfg->dtype);
   if (!w->h_layers) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_create: weights.h_layers is null");
@@ -698,8 +703,19 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
     if (rc) return rc;
     float* cls = reinterpret_cast<float*>(ws + wl.cls);
     float* y = reinterpret_cast<float*>(ws + wl.y);
-    opv::rank_head_cls_ln_kernel<<<n_seqs, 32, 0, stream>>>(h, d_cu_seqlens, e->w.d_final_norm, cls, H, c.norm_eps);
-    OPV_LAUNCH_CHECK("rank_head_cls_ln_kernel");
+    if (c.classifier_pooling) {
+      float* partial = reinterpret_cast<float*>(ws + wl.pool);
+      dim3 grid((max_seqlen + opv::kPoolChunkRows - 1) / opv::kPoolChunkRows, n_seqs);
+      OPV_DISPATCH_VEC(H, opv::rank_head_mean_partial_kernel<VEC><<<grid, opv::kRowWarps * 32, 0, stream>>>(
+                              h, d_cu_seqlens, e->w.d_final_norm, partial, c.norm_eps));
+      OPV_LAUNCH_CHECK("rank_head_mean_partial_kernel");
+      opv::rank_head_mean_finish_kernel<<<n_seqs, 128, 0, stream>>>(partial, d_cu_seqlens, cls, H);
+      OPV_LAUNCH_CHECK("rank_head_mean_finish_kernel");
+      e->launches += 1;  // one launch more than the "cls" head
+    } else {
+      opv::rank_head_cls_ln_kernel<<<n_seqs, 32, 0, stream>>>(h, d_cu_seqlens, e->w.d_final_norm, cls, H, c.norm_eps);
+      OPV_LAUNCH_CHECK("rank_head_cls_ln_kernel");
+    }
     {
       dim3 grid(H / opv::kRankFeatTile, (n_seqs + opv::kRankSeqTile - 1) / opv::kRankSeqTile);
       const size_t smem = static_cast<size_t>(opv::kRankSeqTile) * H * sizeof(float);

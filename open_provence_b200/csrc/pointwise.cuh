@@ -149,8 +149,8 @@ final_ln_prune_kernel(const float* __restrict__ h, const float* __restrict__ w, 
   }
 }
 
-// K13: rank_logits[s] = classifier(LN(gelu(dense(LN(h[cls_s]; final_norm))); head.norm)) (HF:621-634,493-502),
-// "cls" pooling only.  Three small launches: the first version ran everything in one CTA per sequence and spent
+// K13: rank_logits[s] = classifier(LN(gelu(dense(pooled[s])); head.norm)) (HF:621-634,493-502) with
+// pooled[s] = LN(h[cls_s]; final_norm) for "cls" pooling (mean pooling: further down).  Three small launches: the first version ran everything in one CTA per sequence and spent
 // 337 us per step re-reading the [H, H] dense matrix once per sequence with one dependent load at a time.
 //   stage 1 (one warp per sequence)      cls[s]  = LN(h[first token of s]; final_norm)
 //   stage 2 (8 features x 8 sequences)   y[s][j] = gelu(cls[s] . dense[j])   dense row held in registers,
@@ -175,6 +175,72 @@ rank_head_cls_ln_kernel(const float* __restrict__ h, const int32_t* __restrict__
   }
   const float rstd = 1.0f / sqrtf(warp_sum(part) * inv_h + eps);
   for (int i = lane; i < H; i += 32) cls[static_cast<int64_t>(s) * H + i] = (row[i] - mean) * rstd * final_norm[i];
+}
+
+// classifier_pooling = "mean" (HF:623-630): pooled[s] = (1 / n_s) * sum over the sequence's tokens of
+// LN(h[t]; final_norm), in place of the CLS row.  Two launches, summation order fixed by the sequence alone (so the
+// result does not depend on what else is in the batch):
+//   partial  grid (chunks, sequences): the 8 warps of a CTA walk a chunk of kPoolChunkRows rows (warp w takes rows
+//            w, w + 8, ...), each lane accumulating its 4 * VEC columns; the warps' sums are added in warp order
+//   finish   one CTA per sequence adds the chunk sums in chunk order and divides by n_s
+// A chunk's slot in `partial` is begin / kPoolChunkRows + s + chunk: unique per (s, chunk) because
+// floor(n / C) + 1 >= ceil(n / C), and below T / C + n_seqs + 1.
+constexpr int kPoolChunkRows = 256;
+
+template <int VEC>  // H = VEC * 128
+__global__ void __launch_bounds__(kRowWarps * 32)
+rank_head_mean_partial_kernel(const float* __restrict__ h, const int32_t* __restrict__ cu_seqlens,
+                              const float* __restrict__ final_norm, float* __restrict__ partial, const float eps) {
+  constexpr int H = VEC * 128;
+  __shared__ float4 sm_acc[kRowWarps][VEC * 32];
+  const int s = blockIdx.y, chunk = blockIdx.x;
+  const int begin = cu_seqlens[s], n = cu_seqlens[s + 1] - begin;
+  const int r0 = chunk * kPoolChunkRows;
+  if (r0 >= n) return;
+  const int r1 = min(n, r0 + kPoolChunkRows);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0 + warp; r < r1; r += kRowWarps) {
+    float4 v[VEC];
+    load_row_f32<VEC>(h + static_cast<int64_t>(begin + r) * H, lane, v);
+    float mean, rstd;
+    row_norm_stats<VEC>(v, eps, mean, rstd);
+    row_normalize<VEC>(v, final_norm, lane, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      acc[i].x += v[i].x, acc[i].y += v[i].y, acc[i].z += v[i].z, acc[i].w += v[i].w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) sm_acc[warp][i * 32 + lane] = acc[i];
+  __syncthreads();
+  float* out = partial + (static_cast<int64_t>(begin / kPoolChunkRows) + s + chunk) * H;
+  for (int i = threadIdx.x; i < VEC * 32; i += blockDim.x) {
+    float4 t = sm_acc[0][i];
+#pragma unroll
+    for (int w = 1; w < kRowWarps; ++w) {
+      const float4 u = sm_acc[w][i];
+      t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
+    }
+    *reinterpret_cast<float4*>(out + i * 4) = t;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+rank_head_mean_finish_kernel(const float* __restrict__ partial, const int32_t* __restrict__ cu_seqlens,
+                             float* __restrict__ pooled, const int H) {
+  const int s = blockIdx.x;
+  const int begin = cu_seqlens[s], n = cu_seqlens[s + 1] - begin;
+  const int chunks = (n + kPoolChunkRows - 1) / kPoolChunkRows;
+  const float* src = partial + (static_cast<int64_t>(begin / kPoolChunkRows) + s) * H;
+  const float inv_n = 1.0f / static_cast<float>(n > 0 ? n : 1);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    float t = 0.f;
+    for (int c = 0; c < chunks; ++c) t += src[static_cast<int64_t>(c) * H + i];
+    pooled[static_cast<int64_t>(s) * H + i] = t * inv_n;
+  }
 }
 
 template <int VEC>  // H = VEC * 128

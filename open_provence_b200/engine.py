@@ -94,8 +94,10 @@ class Engine:
         model_type = backbone_cfg.get("model_type", "modernbert")
         if model_type != "modernbert":
             raise NotImplementedError(f"unsupported backbone architecture {model_type!r}: only ModernBERT is implemented")
-        if backbone_cfg.get("classifier_pooling", "cls") != "cls":
-            raise NotImplementedError("classifier_pooling='mean' is not implemented (published checkpoints use 'cls')")
+        pooling = backbone_cfg.get("classifier_pooling", "cls")  # configuration_modernbert.py: "cls" | "mean"
+        if pooling not in ("cls", "mean"):
+            raise ValueError(f'classifier_pooling must be "cls" or "mean", got {pooling!r}')
+        self.classifier_pooling = pooling
         for flag in ("attention_bias", "mlp_bias", "norm_bias", "classifier_bias"):
             if backbone_cfg.get(flag, False):
                 raise NotImplementedError(f"ModernBERT option {flag}=True is not implemented")
@@ -196,6 +198,7 @@ class Engine:
         cfg.norm_eps = self.eps
         cfg.dtype = self.dtype_code
         cfg.fuse_epilogues = 1 if self.fused else 0
+        cfg.classifier_pooling = 1 if self.classifier_pooling == "mean" else 0
         if self.layers > N.OPV_MAX_LAYERS:
             raise NotImplementedError(f"at most {N.OPV_MAX_LAYERS} layers are supported")
         for l, flag in enumerate(self.global_flags):

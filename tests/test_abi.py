@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     missing = [n for n in _declared_functions() if not hasattr(lib, n)]
     assert not missing, f"symbols declared in include/opv.h but not exported: {missing}"
     lib.opv_abi_version.restype = ctypes.c_int
-    assert lib.opv_abi_version() == 1
+    assert lib.opv_abi_version() == 2
 
 
 def test_binding_covers_every_declared_symbol(lib_path):

@@ -148,3 +148,14 @@ def test_programmatic_dependent_launch_is_bit_identical(name):
             ops.set_option("pdl_max_tokens", 32768)
     for prune, rank in outs[1:]:
         assert np.array_equal(prune, outs[0][0]) and np.array_equal(rank, outs[0][1])
+
+
+@pytest.mark.parametrize("name", ["xsmall-30M", "en-gte-149M"])
+def test_family_mean_pooling_fp32(name):
+    """classifier_pooling = "mean" at H = 256 / 768 against the fp64 oracle."""
+    cfg, sd, seqs = _case(name)
+    cfg["classifier_pooling"] = "mean"
+    w64 = {k: v.double().numpy() for k, v in sd.items()}
+    ref_rank, _ = onp.forward_batch(seqs, w64, cfg)
+    _, rank = _run(cfg, sd, seqs, "fp32")
+    assert np.abs(rank - ref_rank).max() < 1e-5

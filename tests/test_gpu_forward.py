@@ -99,3 +99,47 @@ def test_bf16_engine_against_the_references_own_bf16_forward(tiny_ckpt_dir, tiny
           f"prune {ref_prune_err:.3e} | engine vs reference bf16 prune {to_ref_prune:.3e}")
     assert ours_prune <= ref_prune_err and ours_rank <= max(ref_rank_err, 5e-3)
     assert to_ref_prune <= 2 * ref_prune_err
+
+
+# ---- classifier_pooling = "mean" (HF:623-630; ModernBERT-base derived checkpoints) ------------------------------
+def _mean_fixture(tiny_ckpt_dir):
+    data = np.load(tiny_ckpt_dir.parent / "forward_tiny_mean.npz")
+    lengths = data["lengths"].tolist()
+    ids = torch.from_numpy(data["input_ids"].astype(np.int32)).to(DEV)
+    cu = torch.from_numpy(np.concatenate([[0], np.cumsum(lengths)]).astype(np.int32)).to(DEV)
+    return data, ids, cu, lengths
+
+
+def test_mean_pooling_fp32_matches_reference_1e5(tiny_ckpt_dir, tiny_config):
+    """Reference forward with classifier_pooling="mean" (tests/golden/make_golden_mean.py): sequences of 1 ... 1024
+    tokens, i.e. one to four 256-row chunks of the pooling kernel."""
+    data, ids, cu, lengths = _mean_fixture(tiny_ckpt_dir)
+    cfg = dict(tiny_config["base_model_config"], classifier_pooling="mean")
+    eng = Engine(cfg, _state_dict(tiny_ckpt_dir), device=DEV, dtype="fp32", num_labels=1)
+    prune, rank = eng.forward_packed(ids, cu, max(lengths))
+    torch.cuda.synchronize()
+    e_rank = np.abs(rank.cpu().double().numpy() - data["ranking_logits_f64"]).max()
+    e_prune = np.abs(prune.cpu().double().numpy() - data["pruning_logits_f64"]).max()
+    print(f"mean pooling, fp32 engine vs fp64 reference: rank {e_rank:.3e} prune {e_prune:.3e}")
+    assert e_rank < 1e-5 and e_prune < 2e-5
+    # and it is not the CLS head by accident
+    cls = Engine(tiny_config["base_model_config"], _state_dict(tiny_ckpt_dir), device=DEV, dtype="fp32", num_labels=1)
+    _, rank_cls = cls.forward_packed(ids, cu, max(lengths))
+    assert np.abs(rank_cls.cpu().double().numpy() - data["ranking_logits_f64"])[1:].max() > 1e-3
+    assert abs(float(rank_cls[0, 0]) - float(data["ranking_logits_f64"][0, 0])) < 1e-5  # one token: mean == cls
+
+
+def test_mean_pooling_bf16_and_batch_invariance(tiny_ckpt_dir, tiny_config):
+    data, ids, cu, lengths = _mean_fixture(tiny_ckpt_dir)
+    cfg = dict(tiny_config["base_model_config"], classifier_pooling="mean")
+    eng = Engine(cfg, _state_dict(tiny_ckpt_dir), device=DEV, dtype="bf16", num_labels=1)
+    prune, rank = eng.forward_packed(ids, cu, max(lengths))
+    torch.cuda.synchronize()
+    assert np.abs(rank.cpu().double().numpy() - data["ranking_logits_f64"]).max() < 2e-2
+    # every sequence alone gives the same bits as inside the batch (summation order depends on the sequence only)
+    bounds = cu.cpu().numpy()
+    for s in (0, 3, 5, 8):
+        one = ids[bounds[s] : bounds[s + 1]].contiguous()
+        cu1 = torch.tensor([0, one.numel()], dtype=torch.int32, device=DEV)
+        p1, r1 = eng.forward_packed(one, cu1, int(one.numel()))
+        assert torch.equal(r1[0], rank[s]) and torch.equal(p1, prune[bounds[s] : bounds[s + 1]])

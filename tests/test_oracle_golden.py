@@ -64,3 +64,20 @@ def test_flops_formula_matches_baseline_table():
     assert abs(onp.algorithmic_flops_per_pair(xsmall, 512) / 1e9 - 12.19) < 0.01
     large = dict(hidden_size=768, num_hidden_layers=25, intermediate_size=3072, num_labels=1, local_attention=128)
     assert abs(onp.algorithmic_flops_per_pair(large, 4096) / 1e9 - 2422.37) < 0.01
+
+
+def test_oracle_mean_pooling_matches_reference_fp64(tiny_weights, tiny_config):
+    """classifier_pooling = "mean" (HF:623-630) against the reference run with that backbone config
+    (tests/golden/make_golden_mean.py)."""
+    from pathlib import Path
+
+    data = np.load(Path(__file__).resolve().parent / "golden" / "forward_tiny_mean.npz")
+    cfg = dict(tiny_config["base_model_config"], classifier_pooling="mean")
+    cu = np.concatenate([[0], np.cumsum(data["lengths"])])
+    seqs = [data["input_ids"][cu[i] : cu[i + 1]].tolist() for i in range(len(data["lengths"]))]
+    rank, prunes = onp.forward_batch(seqs, onp.cast_weights(tiny_weights, np.float64), cfg)
+    assert np.abs(rank - data["ranking_logits_f64"]).max() < 1e-9
+    # positions up to 1023: HF's fp32 RoPE angles (HF:162-172) leave 2e-9 on the token logits
+    assert np.abs(np.concatenate(prunes) - data["pruning_logits_f64"]).max() < 1e-8
+    cls_rank, _ = onp.forward_batch(seqs[-2:], onp.cast_weights(tiny_weights, np.float64), tiny_config["base_model_config"])
+    assert np.abs(cls_rank - data["ranking_logits_f64"][-2:]).max() > 1e-3  # the fixture does distinguish the poolings
