@@ -127,7 +127,8 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
  * tiles (default), 0 = single-CTA kernel.  "gemm_group_rows": row-grouped tile order of the RoPE GEMM (default 1).
  * "pdl": 1 = GEMM / attention / LayerNorm kernels are launched with programmatic stream serialization so that each
  * kernel's prologue overlaps its predecessor's tail (default), 0 = plain stream order; "pdl_max_tokens": forwards
- * with more packed tokens than this are launched without it (default 32768, profiles/r1t_pdl.md). */
+ * with more packed tokens than this do not release their dependents early (default 32768, profiles/r1t_pdl.md);
+ * "pdl_late": 0 = such forwards are launched without the attribute altogether (default 1). */
 int opv_set_option(const char* name, int64_t value);
 
 /* Per-kernel-class timing of the forward, measured with CUDA events on the launch stream.

@@ -51,7 +51,8 @@ template <bool P_IN_TMEM>
 __global__ void __launch_bounds__(kFaThreads, 2)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
                          const int32_t* __restrict__ cu_seqlens, const int H, const int half_window,
-                         const int n_seqs, const int tiles_per_seq, long long* __restrict__ trace) {
+                         const int n_seqs, const int tiles_per_seq, long long* __restrict__ trace,
+                         const int pdl_late) {
   // trace (tools/attn_check.py only; nullptr in the product): clock64() stamps of the first tile of CTA 1, 16 slots
   // per key block: softmax warp 0 [0 s_full seen, 1 scores read, 4 pv_done seen, 5 P published], MMA warp
   // [6 S(i) issued, 7 PV(i) issued], softmax warp w < 3 [8+2w scores read, 9+2w P published]; block 0 slots
@@ -135,7 +136,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_launch_dependents();
+  if (!pdl_late) pdl_launch_dependents();
   pdl_wait();  // the prologue above overlapped the previous kernel; qkv is visible from here on
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for ptxas: a per-thread TMEM address makes every tcgen05.mma an ELECT / R2UR.BROADCAST waterfall loop
 

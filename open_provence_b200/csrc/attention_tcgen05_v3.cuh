@@ -35,7 +35,7 @@ struct Fa3SmemLayout {
 __global__ void __launch_bounds__(kFa3Threads, 2)
 attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
                             const int32_t* __restrict__ cu_seqlens, const int H, const int half_window,
-                            const int n_seqs, const int tiles_per_seq) {
+                            const int n_seqs, const int tiles_per_seq, const int pdl_late) {
   using L = Fa3SmemLayout;
   const int heads = H / 64;
   const int total_tiles = n_seqs * heads * tiles_per_seq;
@@ -106,7 +106,7 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_launch_dependents();
+  if (!pdl_late) pdl_launch_dependents();
   pdl_wait();  // the prologue above overlapped the previous kernel; qkv is visible from here on
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform (single UTCHMMA per MMA)
 

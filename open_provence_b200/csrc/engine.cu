@@ -113,6 +113,12 @@ int g_pdl = 1;
 // kernels run), so it is applied to forwards of at most this many tokens.
 long long g_pdl_max_tokens = 32768;
 thread_local long long t_forward_tokens = 0;  // tokens of the forward being enqueued (0 outside opv_forward_packed)
+// 1 = forwards ABOVE g_pdl_max_tokens also get the attribute, but their GEMM / attention kernels do not release the
+// dependent early (it launches when the last CTA exits), so nothing is parked on the SMs and only the launch gap is
+// hidden: 30.50 / 30.38 -> 30.23 / 30.28 ms per 131072-token step (profiles/r1t_pdl.md).
+int g_pdl_late = 1;
+inline bool pdl_attr_on() { return g_pdl && (t_forward_tokens <= g_pdl_max_tokens || g_pdl_late); }
+inline int pdl_late_flag() { return t_forward_tokens > g_pdl_max_tokens ? 1 : 0; }
 
 // Launch through cudaLaunchKernelEx so that the PDL attribute can ride along.  Only for kernels that call
 // opv::pdl_wait() before their first global-memory access.
@@ -128,7 +134,7 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (g_pdl && t_forward_tokens <= g_pdl_max_tokens) ? 1 : 0;
+  cfg.numAttrs = pdl_attr_on() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -182,8 +188,10 @@ int launch_gemm_tc(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUten
                    const opv::GemmEpilogueArgs& ep, int64_t M, int N, int K, cudaStream_t stream) {
   const int64_t tiles = ((M + opv::kGemmBlockM - 1) / opv::kGemmBlockM) * (N / BLOCK_N);
   const int grid = static_cast<int>(tiles < g_num_sms ? tiles : g_num_sms);
+  opv::GemmEpilogueArgs ep_launch = ep;
+  ep_launch.pdl_late = pdl_late_flag();
   launch_pdl(opv::gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>, dim3(grid), dim3(opv::gemm_threads(EPI)),
-             opv::GemmSmemLayout<BLOCK_N, EPI>::kTotal, stream, tm_a, tm_b, tm_c, ep, (int)M, N, K);
+             opv::GemmSmemLayout<BLOCK_N, EPI>::kTotal, stream, tm_a, tm_b, tm_c, ep_launch, (int)M, N, K);
   OPV_LAUNCH_CHECK("gemm_bf16_tcgen05_kernel");
   return OPV_OK;
 }
@@ -197,6 +205,7 @@ int launch_gemm_pair(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUt
   const int clusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
   opv::GemmEpilogueArgs ep_launch = ep;
   ep_launch.group_rows = (EPI == opv::kEpiRope && g_gemm_group_rows && pairs_m >= 4 * clusters) ? 1 : 0;
+  ep_launch.pdl_late = pdl_late_flag();
   launch_pdl(opv::gemm_bf16_tcgen05_pair_kernel<EPI>, dim3(2 * clusters), dim3(opv::gemm_threads(EPI)),
              opv::GemmPairSmemLayout<EPI>::kTotal, stream, tm_a, tm_b, tm_c, ep_launch, (int)M, N, K);
   OPV_LAUNCH_CHECK("gemm_bf16_tcgen05_pair_kernel");
@@ -322,15 +331,16 @@ int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, i
     // for sliding-window layers (0.156 vs 0.176 ms per layer at 64 x 2048); 3 / 4 force one of them everywhere
     if (g_attention_impl == 3 || (g_attention_impl == 1 && half_window >= 0))
       launch_pdl(opv::attention_tcgen05_v3_kernel, dim3(grid), dim3(opv::kFa3Threads), opv::Fa3SmemLayout::kTotal, s,
-                 *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq);
+                 *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq,
+                 pdl_late_flag());
     else if (g_attention_impl == 1 || g_attention_impl == 4)
       launch_pdl(opv::attention_tcgen05_kernel<true>, dim3(grid), dim3(opv::kFaThreads), opv::FaSmemLayout<true>::kTotal,
                  s, *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq,
-                 g_attention_trace);
+                 g_attention_trace, pdl_late_flag());
     else
       launch_pdl(opv::attention_tcgen05_kernel<false>, dim3(grid), dim3(opv::kFaThreads),
                  opv::FaSmemLayout<false>::kTotal, s, *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window,
-                 n_seqs, tiles_per_seq, g_attention_trace);
+                 n_seqs, tiles_per_seq, g_attention_trace, pdl_late_flag());
     OPV_LAUNCH_CHECK("attention_tcgen05_kernel");
   } else if (dtype == OPV_DTYPE_BF16) {
     dim3 grid((max_seqlen + opv::kAttBlockM - 1) / opv::kAttBlockM, heads, n_seqs);
@@ -875,6 +885,10 @@ int opv_set_option(const char* name, int64_t value) {
   }
   if (strcmp(name, "pdl") == 0) {
     g_pdl = value != 0;
+    return OPV_OK;
+  }
+  if (strcmp(name, "pdl_late") == 0) {
+    g_pdl_late = value != 0;
     return OPV_OK;
   }
   if (strcmp(name, "pdl_max_tokens") == 0) {

@@ -44,6 +44,7 @@ struct GemmEpilogueArgs {
   // block, so the rows' cos|sin table lines are staged once per row block instead of once per rotated tile
   // (set by the host when there are at least as many row blocks as clusters)
   int32_t group_rows;
+  int32_t pdl_late;  // 1 = do not release the dependent kernel early (large forwards, see engine.cu g_pdl_late)
 };
 
 // ROPE epilogue: the cos|sin rows (2 x 128 B) of the tile's 128 tokens are staged in shared memory by
@@ -250,7 +251,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_launch_dependents();
+  if (!ep.pdl_late) pdl_launch_dependents();
   pdl_wait();  // the prologue above overlapped the previous kernel; its outputs are visible from here on
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for ptxas: a per-thread TMEM address makes every tcgen05.mma an ELECT / R2UR.BROADCAST waterfall loop
 
@@ -434,7 +435,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
   tc_fence_before();
   cluster_sync_all();  // barrier inits of both CTAs visible before any remote arrive / multicast commit
   tc_fence_after();
-  pdl_launch_dependents();
+  if (!ep.pdl_late) pdl_launch_dependents();
   pdl_wait();  // the prologue above overlapped the previous kernel; its outputs are visible from here on
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for ptxas: a per-thread TMEM address makes every tcgen05.mma an ELECT / R2UR.BROADCAST waterfall loop
 

@@ -139,13 +139,18 @@ def test_programmatic_dependent_launch_is_bit_identical(name):
 
     cfg, sd, seqs = _case(name)
     outs = []
-    for option, value in (("pdl", 1), ("pdl", 0), ("pdl_max_tokens", 0)):
-        ops.set_option(option, value)
+    # early release (default for small forwards) | no PDL | late release (what large forwards get) | attribute off above
+    # the token threshold
+    for options in ((("pdl", 1),), (("pdl", 0),), (("pdl_max_tokens", 0), ("pdl_late", 1)),
+                    (("pdl_max_tokens", 0), ("pdl_late", 0))):
+        for option, value in options:
+            ops.set_option(option, value)
         try:
             outs.append(_run(cfg, sd, seqs, "bf16"))
         finally:
             ops.set_option("pdl", 1)
             ops.set_option("pdl_max_tokens", 32768)
+            ops.set_option("pdl_late", 1)
     for prune, rank in outs[1:]:
         assert np.array_equal(prune, outs[0][0]) and np.array_equal(rank, outs[0][1])
 
