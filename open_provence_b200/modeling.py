@@ -17,7 +17,6 @@ of the reference's per-block dictionaries so one ``process()`` call costs a hand
 from __future__ import annotations
 
 import json
-import os
 from collections.abc import Callable, Mapping, Sequence
 from dataclasses import dataclass, field
 from pathlib import Path
@@ -865,8 +864,17 @@ class OpenProvenceModel:
         # waits for the GPU.  (The reference streams its jobs through a DataLoader for the same reason,
         # standalone:3510-3605.)  One chunk when the input is small.
         all_pairs = [(qi, ci) for qi in range(len(queries)) for ci in range(len(contexts[qi]))]
-        chunk_size = max(1, int(preprocess_batch_size)) if preprocess_batch_size else 64
-        chunks = [all_pairs[i : i + chunk_size] for i in range(0, len(all_pairs), chunk_size)] or [[]]
+        if preprocess_batch_size:
+            chunk_size = max(1, int(preprocess_batch_size))
+            chunks = [all_pairs[i : i + chunk_size] for i in range(0, len(all_pairs), chunk_size)] or [[]]
+        else:
+            # 16, 32, 64, 64, ... contexts: the device is idle while the first chunk is prepared, so that one is small
+            chunks, at, size = [], 0, 16
+            while at < len(all_pairs):
+                chunks.append(all_pairs[at : at + size])
+                at += size
+                size = min(64, size * 2)
+            chunks = chunks or [[]]
         query_tokens = [[int(t) for t in self.tokenizer.encode(q, add_special_tokens=False)] for q in queries]
         stage = {"assembly": 0.0, "inference": 0.0}
 
