@@ -4,3 +4,4 @@
 set -u
 compute-sanitizer --tool memcheck --print-limit 5 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_families.py -m gpu -x -q -k "xsmall and bf16" 2>&1 | tail -4
+compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_forward.py -m gpu -x -q -k "mean" 2>&1 | tail -4
