@@ -101,8 +101,9 @@ def _as_ptr(array: np.ndarray | None) -> int | None:
 def _copy(ptr: int | None, n: int, dtype: Any) -> np.ndarray:
     if not ptr or n <= 0:
         return np.zeros(0, dtype=dtype)
-    ctype = np.ctypeslib.as_ctypes_type(np.dtype(dtype))
-    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)).copy()
+    out = np.empty(n, dtype=dtype)
+    C.memmove(out.ctypes.data, ptr, out.nbytes)
+    return out
 
 
 class PackedBlocks:

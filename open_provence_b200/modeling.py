@@ -16,6 +16,7 @@ of the reference's per-block dictionaries so one ``process()`` call costs a hand
 
 from __future__ import annotations
 
+import contextlib
 import json
 from collections.abc import Callable, Mapping, Sequence
 from dataclasses import dataclass, field
@@ -765,6 +766,15 @@ class OpenProvenceModel:
             p.n_fragments, p.n_blocks = len(p.fragments), len(p.blocks)
         return table
 
+    def _sep_token_length(self) -> int:
+        """``len(tokenizer.encode(sep_token))`` (standalone:2232), cached per tokenizer / separator."""
+        sep = getattr(self.tokenizer, "sep_token", None) or ""
+        key = (id(self.tokenizer), sep)
+        cached = getattr(self, "_sep_len_cache", None)
+        if cached is None or cached[0] != key:
+            cached = self._sep_len_cache = (key, len(self.tokenizer.encode(sep, add_special_tokens=False)))
+        return cached[1]
+
     def _pack_template(self):
         """Special-token template for the native packer, derived once per tokenizer state."""
         key = (id(self.tokenizer), self._manual_special_tokens_required, self._manual_cls_token_id,
@@ -857,7 +867,7 @@ class OpenProvenceModel:
         queries, contexts, structure = self._normalize_inputs(question, context)
         contexts, titles = self._resolve_titles(queries, contexts, title, first_line_as_title=first_line_as_title)
         max_fragment_tokens = max(16, self.max_length - 2) if respect_sentence_boundaries else max(16, self.max_length // 2)
-        sep_len = len(self.tokenizer.encode(getattr(self.tokenizer, "sep_token", None) or "", add_special_tokens=False))
+        sep_len = self._sep_token_length()
 
         # Host preparation (sentences -> tokens -> fragments -> packed block table) of chunk k+1 runs in a worker
         # thread while the device scores chunk k: the tokenizer releases the GIL, and so does this thread while it
@@ -875,7 +885,7 @@ class OpenProvenceModel:
                 at += size
                 size = min(64, size * 2)
             chunks = chunks or [[]]
-        query_tokens = [[int(t) for t in self.tokenizer.encode(q, add_special_tokens=False)] for q in queries]
+        query_tokens = tokenize_batch(self.tokenizer, queries)  # same ids as tokenizer.encode(q, add_special_tokens=False)
         stage = {"assembly": 0.0, "inference": 0.0}
 
         def prepare(pairs_k):
@@ -898,8 +908,15 @@ class OpenProvenceModel:
         block_base = sentence_base = 0
         from concurrent.futures import ThreadPoolExecutor
 
-        with ThreadPoolExecutor(max_workers=1) as pool:
-            pending = pool.submit(prepare, chunks[0])
+        class _Done:  # a single chunk is prepared inline: starting a worker thread costs more than it hides
+            def __init__(self, value):
+                self._value = value
+
+            def result(self):
+                return self._value
+
+        with ThreadPoolExecutor(max_workers=1) if len(chunks) > 1 else contextlib.nullcontext() as pool:
+            pending = pool.submit(prepare, chunks[0]) if pool is not None else _Done(prepare(chunks[0]))
             for k in range(len(chunks)):
                 plans_k, table_k, t_local, t_asm = pending.result()
                 if k + 1 < len(chunks):
