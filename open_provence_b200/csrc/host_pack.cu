@@ -205,6 +205,15 @@ int validate(const opv_pack_input& in) {
     if (in.h_ctx_sent_offsets[c + 1] < in.h_ctx_sent_offsets[c] || in.h_ctx_prefix[c] < 0)
       return fail(OPV_ERR_INVALID_ARGUMENT, "opv_pack_build: sentence offsets must be non-decreasing");
   }
+  for (int32_t q = 0; q < in.n_queries && in.n_contexts > 0; ++q)
+    if (in.h_query_offsets[q + 1] < in.h_query_offsets[q] || in.h_query_offsets[q] < 0)
+      return fail(OPV_ERR_INVALID_ARGUMENT, "opv_pack_build: query offsets must be non-negative and non-decreasing");
+  if (in.n_contexts > 0 && in.n_queries > 0 && in.h_query_offsets[in.n_queries] > 0 && !in.h_query_tokens)
+    return fail(OPV_ERR_INVALID_ARGUMENT, "opv_pack_build: null query token array");
+  if (in.n_contexts > 0 && (in.h_ctx_sent_offsets[0] < 0 || in.h_sent_offsets[in.h_ctx_sent_offsets[0]] < 0))
+    return fail(OPV_ERR_INVALID_ARGUMENT, "opv_pack_build: offsets must be non-negative");
+  if (in.max_length > (1 << 24) || in.max_fragment_tokens > (1 << 24))
+    return fail(OPV_ERR_INVALID_ARGUMENT, "opv_pack_build: max_length / max_fragment_tokens out of range");
   const int64_t n_sent = in.n_contexts > 0 ? in.h_ctx_sent_offsets[in.n_contexts] : 0;
   for (int64_t s = 0; s < n_sent; ++s)
     if (in.h_sent_offsets[s + 1] < in.h_sent_offsets[s])
