@@ -356,9 +356,16 @@ def tokenize_batch(tokenizer: Any, sentences: Sequence[str]) -> list[list[int]]:
         return []
     backend = _rust_backend(tokenizer)
     if backend is not None:
+        # HF fast tokenizers leave the truncation / padding of their LAST call on the Rust object and never restore
+        # it; ``encode_batch`` would then silently pad every sentence to the longest one or cut it at max_length.
+        # The reference's ``tokenizer(list, add_special_tokens=False)`` resets that state on every call -- so do we.
         try:
+            if backend.truncation is not None:
+                backend.no_truncation()
+            if backend.padding is not None:
+                backend.no_padding()
             return [enc.ids for enc in backend.encode_batch(list(sentences), add_special_tokens=False)]
-        except Exception:  # truncation / padding state on the backend: fall back to the HF call
+        except Exception:  # a backend without these controls: fall back to the HF call
             pass
     enc = tokenizer(list(sentences), add_special_tokens=False, return_attention_mask=False)
     ids = enc.get("input_ids", []) if isinstance(enc, Mapping) or hasattr(enc, "get") else []

@@ -474,10 +474,14 @@ class OpenProvenceModel:
                                  **({"max_length": self.max_length} if truncate else {}))
             return len(enc["input_ids"])
 
-        ranges, prev, acc = [], n_tokens(prefix, False), prefix
+        # call order as in the reference: the truncating calls first, the untruncated prefix call LAST, so the
+        # tokenizer's Rust backend is left without truncation state (fast tokenizers keep the last call's)
+        ends, acc = [], prefix
         for ctx in contexts:
             acc += ctx
-            end = n_tokens(acc, True)
+            ends.append(n_tokens(acc, True))
+        ranges, prev = [], n_tokens(prefix, False)
+        for end in ends:
             ranges.append((prev, end))
             prev = end
         return ranges

@@ -156,3 +156,37 @@ def test_threshold_resolution(tiny_ckpt_dir):
         cfg = OpenProvenceConfig(default_threshold=0.3)
     assert cfg.default_threadshold == pytest.approx(0.3)
     assert OpenProvenceConfig().resolve_default_threshold() == pytest.approx(0.1)
+
+
+@pytest.mark.parametrize("name", ["str_list", "multi_block", "overlong_sentence"])
+def test_process_ignores_tokenizer_state_left_by_earlier_calls(name, process_golden, tiny_ckpt_dir, tiny_tokenizer):
+    """HF fast tokenizers keep the truncation / padding of their last call on the Rust backend.  The reference's
+    ``tokenizer(list, add_special_tokens=False)`` resets it; the Rust ``encode_batch`` fast path must do the same, or
+    every sentence is padded to the longest one / cut at max_length (host_text.tokenize_batch)."""
+    case = next(c for c in process_golden["cases"] if c["name"] == name)
+    model, scorer = _model(tiny_ckpt_dir, tiny_tokenizer, case)
+    kwargs = dict(case["kwargs"])
+    kwargs["sentence_splitter"] = simple_sentence_splitter
+    model.process(**kwargs)  # first call: caches the separator length (a plain tokenizer call that resets the state)
+    scorer.seen.clear()
+    try:
+        tiny_tokenizer(["a b c d e f g h i j k l m n o p", "a"], padding=True, truncation=True, max_length=6)
+        assert tiny_tokenizer.backend_tokenizer.padding is not None
+        assert tiny_tokenizer.backend_tokenizer.truncation is not None
+        result = model.process(**kwargs)
+    finally:
+        tiny_tokenizer.backend_tokenizer.no_padding()
+        tiny_tokenizer.backend_tokenizer.no_truncation()
+    golden = case["result"]
+    assert sorted(scorer.seen) == sorted(tuple(b["ids"]) for b in case["blocks"])
+    assert result["pruned_context"] == golden["pruned_context"]
+    assert result["kept_sentences"] == golden["kept_sentences"]
+
+
+def test_context_ranges_leave_no_truncation_state(tiny_ckpt_dir, tiny_tokenizer, process_golden):
+    case = process_golden["cases"][0]
+    model, _ = _model(tiny_ckpt_dir, tiny_tokenizer, case)
+    model.max_length = 32
+    ranges = model._context_ranges_from_contexts("what is it?", ["Alpha beta gamma. ", "Delta epsilon. " * 20])
+    assert ranges[0][1] == ranges[1][0] and ranges[-1][1] <= 32
+    assert tiny_tokenizer.backend_tokenizer.truncation is None
