@@ -211,6 +211,40 @@ def run_reference(args, world: int, rank: int) -> None:
     emit(line)
 
 
+def parity_against_cpu(cpu: dict, gpu: dict, wl: dict, n_pairs: int) -> dict:
+    """The GPU results of the benchmarked step against the reference's fp32 CPU arithmetic (HF ModernBERT fp32 +
+    numpy prune, ``cpu_baseline`` leg) on the same first ``n_pairs`` blocks: standalone:2893-2924, 3116-3134."""
+    cu = wl["cu_seqlens"]
+    t_end = int(cu[n_pairs])
+    cpu_prune = np.concatenate(cpu["prune_logits"])
+    cpu_rank = np.stack(cpu["rank_logits"]).reshape(n_pairs, -1)
+    frag = np.asarray(cpu["frag_index"], dtype=np.int64)
+    cpu_prob = np.asarray(cpu["sent_prob"], dtype=np.float64)
+    cpu_keep = np.asarray(cpu["keep"], dtype=bool)
+    g_prob, g_keep = gpu["sent_prob"][frag], gpu["keep"][frag]
+    mism = g_keep != cpu_keep
+    band = np.abs(cpu_prob - THRESHOLD) <= 1e-2
+    scale = float(np.abs(cpu_prune).max())
+    return {
+        "against": "reference CPU arithmetic in fp32 (cpu_baseline leg), same blocks, same weights",
+        "blocks": n_pairs,
+        "sentences": int(frag.size),
+        "prune_logit_max_abs": float(np.abs(gpu["prune_logits"][:t_end] - cpu_prune).max()),
+        "prune_logit_mean_abs": float(np.abs(gpu["prune_logits"][:t_end] - cpu_prune).mean()),
+        "prune_logit_scale": scale,
+        "prune_logit_max_rel_to_scale": float(np.abs(gpu["prune_logits"][:t_end] - cpu_prune).max() / scale),
+        "rank_logit_max_abs": float(np.abs(gpu["rank_logits"][:n_pairs].reshape(n_pairs, -1) - cpu_rank).max()),
+        "rank_score_max_abs": float(np.abs(gpu["rank_score"][:n_pairs] - np.asarray(cpu["rank_score"])).max()),
+        "keep_prob_max_abs": float(np.abs(g_prob - cpu_prob).max()),
+        "keep_mismatches": int(mism.sum()),
+        "mismatches_outside_1e-2_band": int((mism & ~band).sum()),
+        "sentences_inside_1e-2_band": int(band.sum()),
+        "kept_fraction_cpu": float(cpu_keep.mean()),
+        "e2e_equals_device_path": bool(np.array_equal(gpu["e2e_keep"], gpu["keep"])
+                                       and np.array_equal(gpu["e2e_sent_prob"], gpu["sent_prob"])),
+    }
+
+
 def main() -> None:
     args = parse_args()
     quiet_stdout()
@@ -323,6 +357,20 @@ def main() -> None:
         e2e_s = float(t.item())
     e2e_value = world * args.batch * args.steps / e2e_s
 
+    # ---- outputs of the benchmarked step itself (device-resident inputs, same kernels) for the in-run parity check
+    gpu_check = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        prune_l, rank_l = eng.forward_packed(d["ids"], d["cu_seqlens"], wl["max_seqlen"])
+        frag_mean, score = eng.fragment_means(prune_l, d["frag_ranges"], rank_l)
+        prob, keep, near = eng.sentence_prune(frag_mean, d["sent_offsets"], d["sent_frag_index"], THRESHOLD)
+        torch.cuda.synchronize(dev)
+        gpu_check = {
+            "prune_logits": prune_l.float().cpu().numpy(), "rank_logits": rank_l.float().cpu().numpy(),
+            "rank_score": score.float().cpu().numpy(), "sent_prob": prob.double().cpu().numpy(),
+            "keep": keep.cpu().numpy().astype(bool), "e2e_keep": out["keep"].numpy().astype(bool),
+            "e2e_sent_prob": out["sent_prob"].double().numpy(),
+        }
+
     # ---- per-kernel-class device times of one step (CUDA events on the launch stream, inside the library)
     eng.profile(True)
     prof_steps = min(3, args.steps)
@@ -375,12 +423,14 @@ def main() -> None:
     }
 
     cpu_baseline = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import hf_cpu_baseline as hb
 
         sd_cpu = syn.random_state_dict(cfg, seed=0)
         model, head = hb.build_hf_model(cfg, sd_cpu)
         res = hb.time_cpu_baseline(model, head, wl, args.cpu_pairs, THRESHOLD, warmup_pairs=1)
+        parity = parity_against_cpu(res["results"], gpu_check, wl, args.cpu_pairs)
         cpu_baseline = {
             "value": round(res["pairs_per_s"], 4),
             "unit": UNIT,
@@ -418,6 +468,7 @@ def main() -> None:
         "roofline": roofline,
         "profile_ms_per_step": profile_ms,
         "cpu_baseline": cpu_baseline,
+        "parity": parity,
     }
     emit(line)
     if world > 1:

@@ -119,10 +119,13 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
                        int64_t n_tokens, int32_t max_seqlen, float* d_prune_logits, float* d_rank_logits,
                        void* d_workspace, size_t workspace_bytes, void* stream);
 
-/* Process-wide tuning switches (tests, profiling).  "attention_impl": bf16 attention kernel,
- * 0 = mma.sync flash kernel (v1), 1 = tcgen05 (default: one softmax thread per query row for global layers, two
- * per row for sliding-window layers), 2 = one thread per row with P staged through shared memory, 3 = two
- * threads per row everywhere, 4 = one thread per row everywhere.  "attention_trace_ptr": device buffer for the clock64() timeline of
+/* Tuning switches (tests, profiling).  opv_set_option() edits the process-wide DEFAULTS: every engine snapshots them
+ * at opv_create(), the single-op entry points (opv_op_*) read them at call time; opv_engine_set_option() changes one
+ * engine only (everything except "gemm_pair", which is fixed at creation).  Both are thread-safe.
+ * "attention_impl": bf16 attention kernel, 1 = default (two-Q-tile ping-pong kernel, one CTA per SM, for global
+ * layers; two softmax threads per query row for sliding-window layers), 2 = one thread per row with P staged through
+ * shared memory, 3 = two threads per row everywhere, 4 = one thread per row, two CTAs per SM, everywhere,
+ * 5 = two-Q-tile kernel everywhere.  "attention_trace_ptr": device buffer for the clock64() timeline of
  * tools/attn_check.py (0 = off, the product setting).  "gemm_pair": 1 = CTA-pair (cta_group::2) GEMM for 256-wide
  * tiles (default), 0 = single-CTA kernel.  "gemm_group_rows": row-grouped tile order of the RoPE GEMM (default 1).
  * "pdl": 1 = GEMM / attention / LayerNorm kernels are launched with programmatic stream serialization so that each
@@ -130,6 +133,7 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
  * with more packed tokens than this do not release their dependents early (default 32768, profiles/r1t_pdl.md);
  * "pdl_late": 0 = such forwards are launched without the attribute altogether (default 1). */
 int opv_set_option(const char* name, int64_t value);
+int opv_engine_set_option(opv_handle engine, const char* name, int64_t value);
 
 /* Per-kernel-class timing of the forward, measured with CUDA events on the launch stream.
  * Enable, run forwards, then collect (synchronises on the recorded events). */

@@ -34,12 +34,26 @@ def sources() -> list[Path]:
     return sorted(CSRC.glob("*.cu"))
 
 
+STAMP_PATH = LIB_DIR / "libopv_sm100.stamp"
+
+
+def source_digest() -> str:
+    """sha256 over the flags and every file the library is compiled from (content, not mtime: a snapshot copy or a
+    checkout changes mtimes without changing sources, and an edited header must always trigger a rebuild)."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "opv.h"]
+    for p in deps:
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not LIB_PATH.exists():
+    if not LIB_PATH.exists() or not STAMP_PATH.exists():
         return True
-    built = LIB_PATH.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "opv.h"]
-    return any(p.stat().st_mtime > built for p in deps)
+    return STAMP_PATH.read_text().strip() != source_digest()
 
 
 def build_native(force: bool = False, verbose: bool = False) -> Path:
@@ -60,6 +74,7 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
         spills = [ln for ln in log.splitlines() if "spill stores" in ln and " 0 bytes spill stores" not in ln]
         if spills and verbose:
             print("register spills:\n" + "\n".join(spills))
+    STAMP_PATH.write_text(source_digest() + "\n")
     if verbose:
         print(f"built {LIB_PATH} ({LIB_PATH.stat().st_size} bytes)")
     return LIB_PATH

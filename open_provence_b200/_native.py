@@ -174,6 +174,7 @@ SIGNATURES = {
         [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
          C.c_void_p]),
     "opv_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+    "opv_engine_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "opv_op_rope": (
         C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "opv_op_geglu": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),

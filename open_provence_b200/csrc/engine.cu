@@ -8,12 +8,14 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/opv.h"
-#include "attention.cuh"
+#include "attention_simt.cuh"
 #include "attention_tcgen05.cuh"
+#include "attention_tcgen05_pp.cuh"
 #include "attention_tcgen05_v3.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -93,32 +95,50 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
   return make_tmap_2d(map, ptr, false, rows, cols, box_rows);
 }
 
-int g_num_sms = 0;
-bool g_attrs_set = false;
-// bf16 attention kernel: 0 = mma.sync v1, 1 = tcgen05 (default: one-thread-per-row kernel for global layers,
-// two-threads-per-row kernel for sliding-window layers), 2 = one-thread-per-row with P in smem,
-// 3 = two-threads-per-row everywhere, 4 = one-thread-per-row (P in TMEM) everywhere
-int g_attention_impl = 1;
-long long* g_attention_trace = nullptr;  // device buffer for clock64() stamps (tools/attn_check.py); nullptr in the product
-// bf16 GEMM with N % 256 == 0: 1 = CTA-pair kernel (cta_group::2, 256 x 256 tiles), 0 = single-CTA kernel
-int g_gemm_pair = 1;
-// ROPE GEMM: 1 = a cluster finishes all column tiles of a row block before the next row block (cos|sin staged once)
-int g_gemm_group_rows = 1;
+// Tuning switches.  ``g_defaults`` is what opv_set_option() edits (under g_mu); every engine takes a snapshot at
+// opv_create() and can be changed alone with opv_engine_set_option(); the single-op entry points (opv_op_*) read the
+// defaults at call time.  Nothing below reads a process-global while launching: each extern "C" entry point copies
+// the options of ITS engine (or the defaults) and the SM count of the CURRENT device into thread-local state.
+struct Options {
+  // bf16 attention kernel: 1 = default (two-Q-tile kernel for global layers, two-threads-per-row kernel for
+  // sliding-window layers), 2 = one-thread-per-row with P in smem, 3 = two-threads-per-row everywhere,
+  // 4 = one-thread-per-row (P in TMEM, 2 CTAs / SM) everywhere, 5 = two-Q-tile kernel everywhere
+  int attention_impl = 1;
+  long long* attention_trace = nullptr;  // device buffer for clock64() stamps (tools/attn_check.py); nullptr in the product
+  // bf16 GEMM with N % 256 == 0: 1 = CTA-pair kernel (cta_group::2, 256 x 256 tiles), 0 = single-CTA kernel
+  int gemm_pair = 1;
+  // ROPE GEMM: 1 = a cluster finishes all column tiles of a row block before the next row block (cos|sin staged once)
+  int gemm_group_rows = 1;
+  // 1 = the kernels that call pdl_wait() (GEMMs, attention, LayerNorm family) are launched with programmatic stream
+  // serialization, so each one's prologue overlaps its predecessor's tail; 0 = plain stream order
+  int pdl = 1;
+  // Measured on B200 (profiles/r1t_pdl.md): PDL takes 18-23 % off a 481-token forward, 12 % off a 2048-token one and
+  // 1.5 % off 32768 tokens, but costs 1.4 % at 65536 and 0.9 % at 131072 tokens (dependents parked on the SMs while
+  // 200-us kernels run), so early release is applied to forwards of at most this many tokens.
+  long long pdl_max_tokens = 32768;
+  // 1 = forwards ABOVE pdl_max_tokens also get the attribute, but their GEMM / attention kernels do not release the
+  // dependent early (it launches when the last CTA exits), so nothing is parked on the SMs and only the launch gap is
+  // hidden: 30.50 / 30.38 -> 30.23 / 30.28 ms per 131072-token step (profiles/r1t_pdl.md).
+  int pdl_late = 1;
+};
 
-// 1 = the kernels that call pdl_wait() (GEMMs, attention, LayerNorm family) are launched with programmatic stream
-// serialization, so each one's prologue overlaps its predecessor's tail; 0 = plain stream order
-int g_pdl = 1;
-// Measured on B200 (profiles/r1t_pdl.md): PDL takes 18-23 % off a 481-token forward, 12 % off a 2048-token one and 1.5 %
-// off 32768 tokens, but costs 1.4 % at 65536 and 0.9 % at 131072 tokens (dependents parked on the SMs while 200-us
-// kernels run), so it is applied to forwards of at most this many tokens.
-long long g_pdl_max_tokens = 32768;
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  bool attrs_set = false;  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is PER DEVICE
+  int num_sms = 0;
+};
+std::mutex g_mu;  // guards g_defaults and g_devices
+Options g_defaults;
+DeviceState g_devices[kMaxDevices];
+
+thread_local Options t_opt;             // options of the call being enqueued
+thread_local int t_num_sms = 0;         // SM count of the device the call runs on
 thread_local long long t_forward_tokens = 0;  // tokens of the forward being enqueued (0 outside opv_forward_packed)
-// 1 = forwards ABOVE g_pdl_max_tokens also get the attribute, but their GEMM / attention kernels do not release the
-// dependent early (it launches when the last CTA exits), so nothing is parked on the SMs and only the launch gap is
-// hidden: 30.50 / 30.38 -> 30.23 / 30.28 ms per 131072-token step (profiles/r1t_pdl.md).
-int g_pdl_late = 1;
-inline bool pdl_attr_on() { return g_pdl && (t_forward_tokens <= g_pdl_max_tokens || g_pdl_late); }
-inline int pdl_late_flag() { return t_forward_tokens > g_pdl_max_tokens ? 1 : 0; }
+#define g_num_sms t_num_sms
+inline bool pdl_attr_on() { return t_opt.pdl && (t_forward_tokens <= t_opt.pdl_max_tokens || t_opt.pdl_late); }
+inline int pdl_late_flag() { return t_forward_tokens > t_opt.pdl_max_tokens ? 1 : 0; }
+
+int set_option_in(Options& o, const char* name, int64_t value);
 
 // Launch through cudaLaunchKernelEx so that the PDL attribute can ride along.  Only for kernels that call
 // opv::pdl_wait() before their first global-memory access.
@@ -152,35 +172,66 @@ int set_gemm_pair_attr() {
   return OPV_OK;
 }
 
+// Per-device one-time setup (function attributes are per device) + the calling thread's launch context.
 int ensure_device_setup() {
-  if (g_attrs_set) return OPV_OK;
   int dev = 0;
   OPV_CUDA(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  OPV_CUDA(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10)
-    return fail(OPV_ERR_UNSUPPORTED, "libopv_sm100 needs an sm_100 (B200) device, found sm_%d%d", prop.major,
-                prop.minor);
-  g_num_sms = prop.multiProcessorCount;
-  if (int rc = set_gemm_attr<256, opv::kEpiStore>()) return rc;
-  if (int rc = set_gemm_attr<256, opv::kEpiRope>()) return rc;
-  if (int rc = set_gemm_attr<256, opv::kEpiResidual>()) return rc;
-  if (int rc = set_gemm_attr<256, opv::kEpiGeglu>()) return rc;
-  if (int rc = set_gemm_attr<128, opv::kEpiStore>()) return rc;
-  if (int rc = set_gemm_attr<128, opv::kEpiRope>()) return rc;
-  if (int rc = set_gemm_attr<128, opv::kEpiResidual>()) return rc;
-  if (int rc = set_gemm_pair_attr<opv::kEpiStore>()) return rc;
-  if (int rc = set_gemm_pair_attr<opv::kEpiRope>()) return rc;
-  if (int rc = set_gemm_pair_attr<opv::kEpiResidual>()) return rc;
-  if (int rc = set_gemm_pair_attr<opv::kEpiGeglu>()) return rc;
-  OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                opv::FaSmemLayout<true>::kTotal));
-  OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                opv::FaSmemLayout<false>::kTotal));
-  OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                opv::Fa3SmemLayout::kTotal));
-  g_attrs_set = true;
+  if (dev < 0 || dev >= kMaxDevices) return fail(OPV_ERR_UNSUPPORTED, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_mu);
+  DeviceState& ds = g_devices[dev];
+  if (!ds.attrs_set) {
+    cudaDeviceProp prop;
+    OPV_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+      return fail(OPV_ERR_UNSUPPORTED, "libopv_sm100 needs an sm_100 (B200) device, found sm_%d%d", prop.major,
+                  prop.minor);
+    if (int rc = set_gemm_attr<256, opv::kEpiStore>()) return rc;
+    if (int rc = set_gemm_attr<256, opv::kEpiRope>()) return rc;
+    if (int rc = set_gemm_attr<256, opv::kEpiResidual>()) return rc;
+    if (int rc = set_gemm_attr<256, opv::kEpiGeglu>()) return rc;
+    if (int rc = set_gemm_attr<128, opv::kEpiStore>()) return rc;
+    if (int rc = set_gemm_attr<128, opv::kEpiRope>()) return rc;
+    if (int rc = set_gemm_attr<128, opv::kEpiResidual>()) return rc;
+    if (int rc = set_gemm_pair_attr<opv::kEpiStore>()) return rc;
+    if (int rc = set_gemm_pair_attr<opv::kEpiRope>()) return rc;
+    if (int rc = set_gemm_pair_attr<opv::kEpiResidual>()) return rc;
+    if (int rc = set_gemm_pair_attr<opv::kEpiGeglu>()) return rc;
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::FaSmemLayout<true>::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::FaSmemLayout<false>::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::Fa3SmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::PpSmemLayout::kTotal));
+    ds.num_sms = prop.multiProcessorCount;
+    ds.attrs_set = true;
+  }
+  t_num_sms = ds.num_sms;
   return OPV_OK;
+}
+
+// Makes `device` current for the duration of an entry point (and restores the caller's device afterwards).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t enter(int device) {
+    cudaError_t err = cudaGetDevice(&prev);
+    if (err != cudaSuccess) return err;
+    if (prev != device) {
+      err = cudaSetDevice(device);
+      switched = err == cudaSuccess;
+    }
+    return err;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+inline Options defaults_snapshot() {
+  std::lock_guard<std::mutex> lock(g_mu);
+  return g_defaults;
 }
 
 template <int BLOCK_N, int EPI>
@@ -204,7 +255,7 @@ int launch_gemm_pair(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUt
   const int max_clusters = g_num_sms / 2;
   const int clusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
   opv::GemmEpilogueArgs ep_launch = ep;
-  ep_launch.group_rows = (EPI == opv::kEpiRope && g_gemm_group_rows && pairs_m >= 4 * clusters) ? 1 : 0;
+  ep_launch.group_rows = (EPI == opv::kEpiRope && t_opt.gemm_group_rows && pairs_m >= 4 * clusters) ? 1 : 0;
   ep_launch.pdl_late = pdl_late_flag();
   launch_pdl(opv::gemm_bf16_tcgen05_pair_kernel<EPI>, dim3(2 * clusters), dim3(opv::gemm_threads(EPI)),
              opv::GemmPairSmemLayout<EPI>::kTotal, stream, tm_a, tm_b, tm_c, ep_launch, (int)M, N, K);
@@ -320,33 +371,40 @@ int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, i
   if (n_seqs <= 0 || max_seqlen <= 0) return OPV_OK;
   if (n_seqs > 65535) return fail(OPV_ERR_UNSUPPORTED, "at most 65535 sequences per launch");
   const int H = heads * 64;
-  if (dtype == OPV_DTYPE_BF16 && g_attention_impl != 0) {
+  if (dtype == OPV_DTYPE_BF16) {
     if (!tm_qkv) return fail(OPV_ERR_INVALID_ARGUMENT, "tcgen05 attention needs the qkv tensor map");
+    const int impl = t_opt.attention_impl;
+    if (impl == 5 || (impl == 1 && half_window < 0)) {
+      // persistent, ONE CTA per SM: (sequence, head, 256-query super tile) list with a grid stride, two Q tiles in flight
+      const int supers_per_seq = (max_seqlen + opv::kPpSuperM - 1) / opv::kPpSuperM;
+      const int64_t total = static_cast<int64_t>(n_seqs) * heads * supers_per_seq;
+      if (total > 0x7fffffffLL) return fail(OPV_ERR_UNSUPPORTED, "too many attention tiles for one launch");
+      const int grid = static_cast<int>(total < g_num_sms ? total : g_num_sms);
+      launch_pdl(opv::attention_tcgen05_pp_kernel, dim3(grid), dim3(opv::kPpThreads), opv::PpSmemLayout::kTotal, s,
+                 *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, supers_per_seq, pdl_late_flag());
+      OPV_LAUNCH_CHECK("attention_tcgen05_pp_kernel");
+      return OPV_OK;
+    }
     // persistent: two CTAs per SM walk the (sequence, head, query tile) list with a grid stride
     const int tiles_per_seq = (max_seqlen + opv::kFaBlockM - 1) / opv::kFaBlockM;
     const int64_t total_tiles = static_cast<int64_t>(n_seqs) * heads * tiles_per_seq;
     if (total_tiles > 0x7fffffffLL) return fail(OPV_ERR_UNSUPPORTED, "too many attention tiles for one launch");
     const int grid = static_cast<int>(total_tiles < 2 * g_num_sms ? total_tiles : 2 * g_num_sms);
-    // default (1): one softmax thread per row for global layers (649 vs 585 TFLOP/s at S = 2048), two threads per row
-    // for sliding-window layers (0.156 vs 0.176 ms per layer at 64 x 2048); 3 / 4 force one of them everywhere
-    if (g_attention_impl == 3 || (g_attention_impl == 1 && half_window >= 0))
+    // sliding-window layers: two softmax threads per row (0.156 vs 0.176 ms per layer at 64 x 2048); 3 / 4 force one
+    // of the 2-CTAs-per-SM kernels everywhere
+    if (impl == 3 || impl == 1)
       launch_pdl(opv::attention_tcgen05_v3_kernel, dim3(grid), dim3(opv::kFa3Threads), opv::Fa3SmemLayout::kTotal, s,
                  *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq,
                  pdl_late_flag());
-    else if (g_attention_impl == 1 || g_attention_impl == 4)
+    else if (impl == 4)
       launch_pdl(opv::attention_tcgen05_kernel<true>, dim3(grid), dim3(opv::kFaThreads), opv::FaSmemLayout<true>::kTotal,
                  s, *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq,
-                 g_attention_trace, pdl_late_flag());
+                 t_opt.attention_trace, pdl_late_flag());
     else
       launch_pdl(opv::attention_tcgen05_kernel<false>, dim3(grid), dim3(opv::kFaThreads),
                  opv::FaSmemLayout<false>::kTotal, s, *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window,
-                 n_seqs, tiles_per_seq, g_attention_trace, pdl_late_flag());
+                 n_seqs, tiles_per_seq, t_opt.attention_trace, pdl_late_flag());
     OPV_LAUNCH_CHECK("attention_tcgen05_kernel");
-  } else if (dtype == OPV_DTYPE_BF16) {
-    dim3 grid((max_seqlen + opv::kAttBlockM - 1) / opv::kAttBlockM, heads, n_seqs);
-    opv::attention_mma_kernel<<<grid, opv::kAttThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv),
-                                                                static_cast<__nv_bfloat16*>(out), cu, H, half_window);
-    OPV_LAUNCH_CHECK("attention_mma_kernel");
   } else {
     dim3 grid((max_seqlen + 3) / 4, heads, n_seqs);
     opv::attention_simt_kernel<float>
@@ -357,6 +415,28 @@ int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, i
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int set_option_in(Options& o, const char* name, int64_t value) {
+  if (strcmp(name, "attention_impl") == 0) {
+    if (value < 1 || value > 5) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_impl must be 1 .. 5");
+    o.attention_impl = static_cast<int>(value);
+  } else if (strcmp(name, "attention_trace_ptr") == 0) {
+    o.attention_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));
+  } else if (strcmp(name, "gemm_group_rows") == 0) {
+    o.gemm_group_rows = value != 0;
+  } else if (strcmp(name, "pdl") == 0) {
+    o.pdl = value != 0;
+  } else if (strcmp(name, "pdl_late") == 0) {
+    o.pdl_late = value != 0;
+  } else if (strcmp(name, "pdl_max_tokens") == 0) {
+    o.pdl_max_tokens = value;
+  } else if (strcmp(name, "gemm_pair") == 0) {
+    o.gemm_pair = value != 0;
+  } else {
+    return fail(OPV_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
+  }
+  return OPV_OK;
+}
 
 }  // namespace
 
@@ -377,8 +457,20 @@ struct opv_engine {
   std::vector<opv_layer_weights> layers;
   std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_wi, tm_wo2;  // bf16 mode only
   bool gemm_pair = true;                                   // CTA-pair GEMM kernel for the 256-wide tiles
+  Options opt;                                             // snapshot of the defaults at opv_create (+ opv_engine_set_option)
   int device;
   size_t elt;  // bytes per operand element
+  // Tensor maps of the activation buffers depend on (workspace address, token count) only: encoded once per
+  // distinct pair instead of on every forward (5 cuTensorMapEncodeTiled calls ~ 10 us of a 1 ms single-pair call).
+  struct ActMaps {
+    const void* ws = nullptr;
+    int64_t tokens = -1;
+    uint64_t stamp = 0;
+    CUtensorMap x, attn, act, qkv, h, u;
+  };
+  ActMaps act_maps[4];
+  uint64_t act_maps_clock = 0;
+  std::mutex mu;  // act_maps, prof, launches
 };
 
 // Counts kernel launches and, when profiling is on, brackets them with CUDA events on the launch stream.
@@ -463,7 +555,8 @@ int opv_create(const opv_config* cfg, const opv_weights* w, int device, opv_hand
   if (cfg->dtype != OPV_DTYPE_BF16 && cfg->dtype != OPV_DTYPE_F32)
     return fail(OPV_ERR_INVALID_ARGUMENT, "unknown dtype %d", cfg->dtype);
   if (!w->h_layers) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_create: weights.h_layers is null");
-  OPV_CUDA(cudaSetDevice(device));
+  DeviceGuard guard;
+  OPV_CUDA(guard.enter(device));
   if (int rc = ensure_device_setup()) return rc;
 
   opv_engine* e = new opv_engine();
@@ -471,7 +564,8 @@ int opv_create(const opv_config* cfg, const opv_weights* w, int device, opv_hand
   e->w = *w;
   e->device = device;
   e->elt = cfg->dtype == OPV_DTYPE_BF16 ? 2 : 4;
-  e->gemm_pair = g_gemm_pair != 0;
+  e->opt = defaults_snapshot();
+  e->gemm_pair = e->opt.gemm_pair != 0;
   e->layers.assign(w->h_layers, w->h_layers + cfg->num_layers);
   e->w.h_layers = e->layers.data();
   const int H = cfg->hidden_size, I = cfg->intermediate_size;
@@ -536,6 +630,10 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
     return fail(OPV_ERR_INVALID_ARGUMENT, "max_seqlen %d outside (0, max_positions=%d]", max_seqlen,
                 e->cfg.max_positions);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceGuard guard;  // the engine's weights, tensor maps and function attributes belong to e->device
+  OPV_CUDA(guard.enter(e->device));
+  if (int rc = ensure_device_setup()) return rc;
+  t_opt = e->opt;
   const opv_config& c = e->cfg;
   const int H = c.hidden_size, I = c.intermediate_size, L = c.num_layers, heads = c.num_heads;
   const int64_t T = n_tokens;
@@ -552,7 +650,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
   int32_t* pos = reinterpret_cast<int32_t*>(ws + wl.pos);
   const int half_window = c.local_window / 2;
   int rc = OPV_OK;
-  struct ForwardTokens {  // launch_pdl() decides per forward whether the PDL attribute pays (g_pdl_max_tokens)
+  struct ForwardTokens {  // launch_pdl() decides per forward whether the PDL attribute pays (pdl_max_tokens)
     explicit ForwardTokens(long long t) { t_forward_tokens = t; }
     ~ForwardTokens() { t_forward_tokens = 0; }
   } forward_tokens(T);
@@ -567,12 +665,29 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
     using bf16 = __nv_bfloat16;
     const bool fused = c.fuse_epilogues != 0;
     CUtensorMap tm_x, tm_attn, tm_act, tm_qkv, tm_h, tm_u;
-    if ((rc = make_tmap_bf16(&tm_qkv, qkv, T, 3 * H, opv::kFaBlockM))) return rc;  // GEMM store + attention loads
-    if ((rc = make_tmap_2d(&tm_h, h, true, T, H, opv::kGemmBlockM))) return rc;     // residual reduce-add
-    if (!fused && (rc = make_tmap_bf16(&tm_u, u, T, 2 * I, opv::kGemmBlockM))) return rc;
-    if ((rc = make_tmap_bf16(&tm_x, x, T, H, opv::kGemmBlockM))) return rc;
-    if ((rc = make_tmap_bf16(&tm_attn, attn, T, H, opv::kGemmBlockM))) return rc;
-    if ((rc = make_tmap_bf16(&tm_act, act, T, I, opv::kGemmBlockM))) return rc;
+    {
+      std::lock_guard<std::mutex> lock(e->mu);
+      opv_engine::ActMaps* slot = nullptr;
+      opv_engine::ActMaps* victim = &e->act_maps[0];
+      for (auto& m : e->act_maps) {
+        if (m.ws == ws && m.tokens == T) slot = &m;
+        if (m.stamp < victim->stamp) victim = &m;
+      }
+      if (!slot) {
+        slot = victim;
+        slot->tokens = -1;  // invalid until every map below is encoded
+        if ((rc = make_tmap_bf16(&slot->qkv, qkv, T, 3 * H, opv::kFaBlockM))) return rc;  // GEMM store + attention loads
+        if ((rc = make_tmap_2d(&slot->h, h, true, T, H, opv::kGemmBlockM))) return rc;     // residual reduce-add
+        if (!fused && (rc = make_tmap_bf16(&slot->u, u, T, 2 * I, opv::kGemmBlockM))) return rc;
+        if ((rc = make_tmap_bf16(&slot->x, x, T, H, opv::kGemmBlockM))) return rc;
+        if ((rc = make_tmap_bf16(&slot->attn, attn, T, H, opv::kGemmBlockM))) return rc;
+        if ((rc = make_tmap_bf16(&slot->act, act, T, I, opv::kGemmBlockM))) return rc;
+        slot->ws = ws;
+        slot->tokens = T;
+      }
+      slot->stamp = ++e->act_maps_clock;
+      tm_x = slot->x, tm_attn = slot->attn, tm_act = slot->act, tm_qkv = slot->qkv, tm_h = slot->h, tm_u = slot->u;
+    }
     {
       LaunchScope sc(e, stream, OPV_PROF_EMBED);
       rc = launch_embed_ln<bf16, bf16>(d_ids, static_cast<const bf16*>(e->w.d_tok_embeddings), e->w.d_emb_norm, h,
@@ -812,6 +927,7 @@ int opv_op_gemm(int32_t dtype, int32_t epilogue, const void* d_a, const void* d_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!d_a || !d_w || !d_c) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_op_gemm: null buffer");
   if (int rc = ensure_device_setup()) return rc;
+  t_opt = defaults_snapshot();
   if (dtype == OPV_DTYPE_F32) {
     if (epilogue == OPV_EPI_STORE)
       return gemm_f32(false, static_cast<const float*>(d_a), static_cast<const float*>(d_w), static_cast<float*>(d_c),
@@ -826,7 +942,7 @@ int opv_op_gemm(int32_t dtype, int32_t epilogue, const void* d_a, const void* d_
   if (bn == 0) return fail(OPV_ERR_UNSUPPORTED, "N = %d does not tile for epilogue %d", n, epilogue);
   CUtensorMap tm_a, tm_b, tm_c;
   if (int rc = make_tmap_bf16(&tm_a, d_a, m, k, opv::kGemmBlockM)) return rc;
-  const bool pair = g_gemm_pair != 0;
+  const bool pair = t_opt.gemm_pair != 0;
   if (int rc = make_tmap_bf16(&tm_b, d_w, n, k, weight_box_rows(bn, pair))) return rc;
   const bool c_f32 = epilogue == OPV_EPI_RESIDUAL;
   if (int rc = make_tmap_2d(&tm_c, d_c, c_f32, m, epilogue == OPV_EPI_GEGLU ? n / 2 : n, opv::kGemmBlockM)) return rc;
@@ -840,6 +956,8 @@ int opv_op_gemm(int32_t dtype, int32_t epilogue, const void* d_a, const void* d_
 int opv_op_layernorm(int32_t dtype, const float* d_h, const float* d_w, void* d_out, int64_t m, int32_t hidden,
                      float eps, void* stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (int rc = ensure_device_setup()) return rc;
+  t_opt = defaults_snapshot();
   if (dtype == OPV_DTYPE_BF16) return launch_layernorm<__nv_bfloat16>(d_h, d_w, static_cast<__nv_bfloat16*>(d_out), m, hidden, eps, s);
   return launch_layernorm<float>(d_h, d_w, static_cast<float*>(d_out), m, hidden, eps, s);
 }
@@ -847,6 +965,8 @@ int opv_op_layernorm(int32_t dtype, const float* d_h, const float* d_w, void* d_
 int opv_op_embed_ln(int32_t dtype, const int32_t* d_ids, const void* d_emb, const float* d_w, float* d_h, void* d_x,
                     int64_t m, int32_t hidden, int32_t vocab, float eps, void* stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (int rc = ensure_device_setup()) return rc;
+  t_opt = defaults_snapshot();
   if (dtype == OPV_DTYPE_BF16)
     return launch_embed_ln<__nv_bfloat16, __nv_bfloat16>(d_ids, static_cast<const __nv_bfloat16*>(d_emb), d_w, d_h,
                                                          static_cast<__nv_bfloat16*>(d_x), m, hidden, vocab, eps, s);
@@ -858,8 +978,9 @@ int opv_op_attention(int32_t dtype, const void* d_qkv, void* d_out, const int32_
                      int64_t n_tokens, int32_t max_seqlen, int32_t num_heads, int32_t half_window, void* stream_) {
   if (!d_qkv || !d_out || !d_cu_seqlens) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_op_attention: null buffer");
   if (int rc = ensure_device_setup()) return rc;
+  t_opt = defaults_snapshot();
   CUtensorMap tm_qkv;
-  const bool tc = dtype == OPV_DTYPE_BF16 && g_attention_impl != 0;
+  const bool tc = dtype == OPV_DTYPE_BF16;
   if (tc) {
     if (n_tokens <= 0) return OPV_OK;
     if (int rc = make_tmap_bf16(&tm_qkv, d_qkv, n_tokens, 3 * num_heads * 64, opv::kFaBlockM)) return rc;
@@ -870,36 +991,16 @@ int opv_op_attention(int32_t dtype, const void* d_qkv, void* d_out, const int32_
 
 int opv_set_option(const char* name, int64_t value) {
   if (!name) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_set_option: null name");
-  if (strcmp(name, "attention_impl") == 0) {
-    if (value < 0 || value > 4) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_impl must be 0 .. 4");
-    g_attention_impl = static_cast<int>(value);
-    return OPV_OK;
-  }
-  if (strcmp(name, "attention_trace_ptr") == 0) {
-    g_attention_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));
-    return OPV_OK;
-  }
-  if (strcmp(name, "gemm_group_rows") == 0) {
-    g_gemm_group_rows = value != 0;
-    return OPV_OK;
-  }
-  if (strcmp(name, "pdl") == 0) {
-    g_pdl = value != 0;
-    return OPV_OK;
-  }
-  if (strcmp(name, "pdl_late") == 0) {
-    g_pdl_late = value != 0;
-    return OPV_OK;
-  }
-  if (strcmp(name, "pdl_max_tokens") == 0) {
-    g_pdl_max_tokens = value;
-    return OPV_OK;
-  }
-  if (strcmp(name, "gemm_pair") == 0) {
-    g_gemm_pair = value != 0;
-    return OPV_OK;
-  }
-  return fail(OPV_ERR_INVALID_ARGUMENT, "unknown option '%s'", name);
+  std::lock_guard<std::mutex> lock(g_mu);
+  return set_option_in(g_defaults, name, value);
+}
+
+int opv_engine_set_option(opv_handle e, const char* name, int64_t value) {
+  if (!e || !name) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_engine_set_option: null argument");
+  if (strcmp(name, "gemm_pair") == 0)
+    return fail(OPV_ERR_INVALID_ARGUMENT, "gemm_pair is fixed at opv_create (the weight tensor maps depend on it)");
+  std::lock_guard<std::mutex> lock(e->mu);
+  return set_option_in(e->opt, name, value);
 }
 
 int opv_op_rope(int32_t dtype, void* d_qkv, const int32_t* d_pos, const float* d_cos, const float* d_sin, int64_t m,

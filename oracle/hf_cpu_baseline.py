@@ -61,12 +61,14 @@ def score_workload(model, head, workload: Mapping[str, Any], pair_slice: slice, 
     """The hot path on CPU for a slice of a synthetic workload: forward, score conversion, sentence prune."""
     cu = workload["cu_seqlens"]
     blocks = list(range(*pair_slice.indices(len(cu) - 1)))
-    results = {"rank_score": [], "sent_prob": [], "keep": []}
+    results = {"rank_score": [], "sent_prob": [], "keep": [], "rank_logits": [], "prune_logits": [], "frag_index": []}
     for at in range(0, len(blocks), batch_size):
         chunk = blocks[at : at + batch_size]
         seqs = [workload["ids"][cu[b] : cu[b + 1]].tolist() for b in chunk]
         rank, prunes = forward_padded(model, head, seqs)
         for b, r, pr in zip(chunk, rank, prunes):
+            results["rank_logits"].append(np.asarray(r, dtype=np.float32))
+            results["prune_logits"].append(np.asarray(pr, dtype=np.float32))
             results["rank_score"].append(opp.ranking_score_from_logits(r))
             probs = opp.keep_probs_from_logits(pr)
             sel = np.nonzero(workload["frag_block"] == b)[0]
@@ -75,6 +77,7 @@ def score_workload(model, head, workload: Mapping[str, Any], pair_slice: slice, 
                 mean = 1.0 if e <= s else float(probs[s:e].mean())
                 mean = max(0.0, min(float(np.mean([mean])), 1.0))
                 results["sent_prob"].append(mean)
+                results["frag_index"].append(int(f))
                 results["keep"].append(mean > threshold)
     return results
 
@@ -84,6 +87,7 @@ def time_cpu_baseline(model, head, workload, n_pairs: int, threshold: float, war
     if warmup_pairs:
         score_workload(model, head, workload, slice(0, warmup_pairs), threshold)
     t0 = time.perf_counter()
-    score_workload(model, head, workload, slice(0, n_pairs), threshold)
+    results = score_workload(model, head, workload, slice(0, n_pairs), threshold)
     dt = time.perf_counter() - t0
-    return {"pairs": n_pairs, "seconds": dt, "pairs_per_s": n_pairs / dt, "threads": torch.get_num_threads()}
+    return {"pairs": n_pairs, "seconds": dt, "pairs_per_s": n_pairs / dt, "threads": torch.get_num_threads(),
+            "results": results}

@@ -45,3 +45,8 @@ def test_engine_arm_line_on_gpu():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(roof) and roof["bound"] in ("hbm", "tensor")
     assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
+    # in-run correctness: the step's GPU outputs against the CPU results the cpu_baseline leg computed
+    par = line["parity"]
+    assert par["blocks"] == 2 and par["sentences"] > 0 and par["e2e_equals_device_path"] is True
+    assert par["mismatches_outside_1e-2_band"] == 0
+    assert par["prune_logit_max_rel_to_scale"] < 1e-2 and par["rank_score_max_abs"] < 1e-2

@@ -2,7 +2,7 @@
 """Correctness + timing of one bf16 attention kernel (run once per impl, each in its own process so that a
 device trap in one variant cannot poison the others).
 
-    python tools/attn_check.py <impl 0|1|2> [half_window] [trace]
+    python tools/attn_check.py <impl 1..5> [half_window] [trace]
 """
 import sys
 from pathlib import Path
