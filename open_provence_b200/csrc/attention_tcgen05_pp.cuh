@@ -41,11 +41,23 @@ struct PpSmemLayout {
   static constexpr int kTotal = kBars + 512 + 1024;                   // + barriers + slack for the 1024 B alignment
 };
 
+// DBG (tools/attn_check.py only; 0 in the product): 1 = FMUL instead of MUFU.EX2, 2 = no tcgen05.ld of the scores,
+// 3 = the MMA warp issues no MMA (commits only), 4 = no row-max exchange between the halves.  Results are wrong by
+// construction; the variants exist to time what is left when one resource is taken out.
+template <int DBG>
 __global__ void __launch_bounds__(kPpThreads, 1)
 attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
                             const int32_t* __restrict__ cu_seqlens, const int H, const int half_window,
-                            const int n_seqs, const int supers_per_seq, const int pdl_late) {
+                            const int n_seqs, const int supers_per_seq, const int pdl_late,
+                            long long* __restrict__ trace) {
+  // trace (tools/attn_check.py only; nullptr in the product): clock64() stamps of CTA 0's first super tile, 32 slots per
+  // key block: softmax thread (tile j, half 0, quarter 0, lane 0) at 8 j + [0 s_full seen, 1 scores loaded, 2 row max
+  // agreed, 3 exponentials done, 4 pv_done seen, 5 P published]; MMA warp 16 + [0 S_A issued, 1 S_B issued, 2 PV_A issued,
+  // 3 PV_B issued]; TMA warp 24 + [0 K(i) requested, 1 V(i) requested]
   using L = PpSmemLayout;
+  bool tracing = trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0;
+#define OPV_PP_STAMP(blk, slot) do { if (tracing) trace[(blk) * 32 + (slot)] = clock64(); } while (0)
+#define OPV_PP_STAMP_F(blk, slot, val) do { if (tracing) { long long t__; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t__), "+f"(val)); trace[(blk) * 32 + (slot)] = t__; } } while (0)
   constexpr int S = kPpKvStages;
   const int heads = H / 64;
   const int total_tiles = n_seqs * heads * supers_per_seq;
@@ -73,6 +85,7 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const bool global = half_window < 0;
+  auto ex2 = [](const float x) { return DBG == 1 ? x * 0.5f : ex2_approx(x); };
 
   // Super tile t -> (sequence, head, 256-row query range); consecutive t are consecutive query ranges of one
   // (sequence, head), so the CTAs running at the same time share K / V in L2.  Key blocks of 128 start at key_base
@@ -139,8 +152,10 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
   pdl_wait();  // the prologue above overlapped the previous kernel; qkv is visible from here on
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform (single UTCHMMA per MMA)
 
+  // Register pool of the CTA = 96 (ptxas cap for 640 threads) x 640 = 61440: 16 softmax warps x 32 x 112 + 4 x 32 x 32.
+  // setmaxnreg.inc only draws from what the CTA's own warps released, never from the SM's unallocated registers.
   if (warp >= 16) {
-    setmaxnreg_dec<40>();
+    setmaxnreg_dec<32>();
     if (warp == 16) {
       // ------------------------------ TMA producer ------------------------------
       if (lane == 0) {
@@ -165,6 +180,7 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
               mbar_expect_tx(&k_full[sg], kFaTileBytes);
               tma_load_2d(sK + sg * kFaTileBytes, &tm_qkv, &k_full[sg], H + st.head * 64,
                           st.begin + st.key_base + i * kFaBlockN);
+              OPV_PP_STAMP(i, 24);
               ++kc;
             }
             if (i >= 1) {
@@ -173,9 +189,11 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
               mbar_expect_tx(&v_full[sg], kFaTileBytes);
               tma_load_2d(sV + sg * kFaTileBytes, &tm_qkv, &v_full[sg], 2 * H + st.head * 64,
                           st.begin + st.key_base + (i - 1) * kFaBlockN);
+              OPV_PP_STAMP(i - 1, 25);
               ++vc;
             }
           }
+          tracing = false;
         }
       }
     } else if (warp == 17) {
@@ -184,6 +202,7 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
       constexpr uint32_t idesc_o = umma_idesc_bf16_f32_bmn(kFaBlockM, 64);     // P.V: V is MN-major
       const uint32_t q_addr = smem_u32(sQ);
       uint32_t td0 = 0, td1 = 0, sc0 = 0, sc1 = 0, pc0 = 0, pc1 = 0, kc = 0, vc = 0;
+      bool tracing_mma = true;
       Super st;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         if (!decode(t, st)) continue;
@@ -200,11 +219,12 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
               if (elect_one()) {
                 const uint32_t t_s = tmem_base + j * 128;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < (DBG == 3 ? 0 : 4); ++k)
                   umma_bf16_ss(t_s, umma_desc_k_sw128(q_addr + j * kFaTileBytes + k * 32),
                                umma_desc_k_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
                 umma_commit(&s_full[j]);
                 if (i == st.hi(j) - 1) umma_commit(&q_empty[j]);
+                if (trace != nullptr && blockIdx.x == 0 && tracing_mma) trace[i * 32 + 16 + j] = clock64();
               }
               __syncwarp();
               ++sc;
@@ -229,9 +249,10 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
                 const uint32_t t_p = tmem_base + 256 + j * 64, t_o = tmem_base + 384 + j * 64;
                 const uint32_t first = b == st.lo(j) ? 0u : 1u;
 #pragma unroll
-                for (int k = 0; k < 8; ++k)  // 16 keys per MMA: two 8-key groups of 1024 B
+                for (int k = 0; k < (DBG == 3 ? 0 : 8); ++k)  // 16 keys per MMA: two 8-key groups of 1024 B
                   umma_bf16_ts(t_o, t_p + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_o, (k != 0) ? 1u : first);
                 umma_commit(&pv_done[j]);
+                if (trace != nullptr && blockIdx.x == 0 && tracing_mma) trace[b * 32 + 18 + j] = clock64();
               }
               __syncwarp();
               ++pc;
@@ -245,6 +266,7 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
         }
         if (st.hi0 > st.lo0) ++td0;
         if (st.hi1 > st.lo1) ++td1;
+        tracing_mma = false;
       }
     }
   } else {
@@ -268,6 +290,8 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
     uint64_t* const my_pv_done = &pv_done[j];
     uint64_t* const my_o_empty = &o_empty[j];
     uint32_t bc = 0;  // running count of this tile's key blocks -> barrier parity
+    tracing = tracing && half == 0 && quarter == 0;
+    const int tslot = 8 * j;
     Super st;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       if (!decode(t, st)) continue;
@@ -297,8 +321,15 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
         }
         mbar_wait(my_s_full, bc & 1);
         tc_fence_after();
+        OPV_PP_STAMP(i, tslot + 0);
         uint32_t sr[64];
-        tmem_ld_32x32b_x64(t_s, sr);
+        if constexpr (DBG == 2) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) sr[c] = __float_as_uint(static_cast<float>((lane * 7 + c * 3 + i) & 31) * 0.01f);
+        } else {
+          tmem_ld_32x32b_x64(t_s, sr);
+        }
+        OPV_PP_STAMP(i, tslot + 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(my_s_empty);  // the MMA warp may overwrite S_j with S_j(i+1)
@@ -317,9 +348,13 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
             mx3 = fmax3(mx3, __uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7]));
           }
           const float mine = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-          my_slots[(bc & 1) * 256] = mine;
-          named_bar_sync(pair_bar, 64);
-          const float mx = fmaxf(mine, other_slots[(bc & 1) * 256]);
+          float mx = mine;
+          if constexpr (DBG != 4) {
+            my_slots[(bc & 1) * 256] = mine;
+            named_bar_sync(pair_bar, 64);
+            mx = fmaxf(mine, other_slots[(bc & 1) * 256]);
+          }
+          OPV_PP_STAMP_F(i, tslot + 2, mx);
           const float m_cand = fmaxf(m_run, mx * scale_log2);  // finite
           upd = (m_cand - m_run) > kFaRescaleThreshold;
           const float m_new = upd ? m_cand : m_run;
@@ -328,10 +363,10 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
           float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
-            const float a = ex2_approx(fmaf(__uint_as_float(sr[2 * c]), scale_log2, -m_new));
-            const float b = ex2_approx(fmaf(__uint_as_float(sr[2 * c + 1]), scale_log2, -m_new));
-            const float e = ex2_approx(fmaf(__uint_as_float(sr[2 * c + 2]), scale_log2, -m_new));
-            const float f = ex2_approx(fmaf(__uint_as_float(sr[2 * c + 3]), scale_log2, -m_new));
+            const float a = ex2(fmaf(__uint_as_float(sr[2 * c]), scale_log2, -m_new));
+            const float b = ex2(fmaf(__uint_as_float(sr[2 * c + 1]), scale_log2, -m_new));
+            const float e = ex2(fmaf(__uint_as_float(sr[2 * c + 2]), scale_log2, -m_new));
+            const float f = ex2(fmaf(__uint_as_float(sr[2 * c + 3]), scale_log2, -m_new));
             sum0 += a, sum1 += b, sum2 += e, sum3 += f;
             pr[c] = pack_bf16x2(a, b);
             pr[c + 1] = pack_bf16x2(e, f);
@@ -373,8 +408,8 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
             } else {
 #pragma unroll
               for (int c = 0; c < 16; ++c) {
-                const float a = ex2_approx(fmaf(__uint_as_float(sr[32 * q + 2 * c]), scale_log2, -m_use));
-                const float b = ex2_approx(fmaf(__uint_as_float(sr[32 * q + 2 * c + 1]), scale_log2, -m_use));
+                const float a = ex2(fmaf(__uint_as_float(sr[32 * q + 2 * c]), scale_log2, -m_use));
+                const float b = ex2(fmaf(__uint_as_float(sr[32 * q + 2 * c + 1]), scale_log2, -m_use));
                 sum0 += a, sum1 += b;
                 pr[16 * q + c] = pack_bf16x2(a, b);
               }
@@ -382,11 +417,13 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
           }
           sum = sum0 + sum1;
         }
+        OPV_PP_STAMP_F(i, tslot + 3, sum);
         l_run = l_run * corr + sum;
 
         if (i > lo) {
           mbar_wait(my_pv_done, (bc - 1) & 1);  // O_j holds blocks < i and the P_j buffer is free again
           tc_fence_after();
+          OPV_PP_STAMP(i, tslot + 4);
           if (__any_sync(0xffffffffu, upd)) {
             uint32_t orr[32];
             tmem_ld_32x32_raw(t_o, orr);
@@ -399,7 +436,9 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(my_p_full);
+        OPV_PP_STAMP(i, tslot + 5);
       }
+      tracing = false;
 
       // epilogue: O / l -> bf16 -> out[begin + row, head*64 + 32*half : +32]
       my_slots[(bc & 1) * 256] = l_run;  // parity of the NEXT block: last used two blocks ago
@@ -432,6 +471,8 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
   tc_fence_before();
   __syncthreads();
   if (warp == 18) tmem_dealloc(tmem_base, kPpTmemCols);
+#undef OPV_PP_STAMP
+#undef OPV_PP_STAMP_F
 }
 
 }  // namespace opv

@@ -104,6 +104,7 @@ struct Options {
   // sliding-window layers), 2 = one-thread-per-row with P in smem, 3 = two-threads-per-row everywhere,
   // 4 = one-thread-per-row (P in TMEM, 2 CTAs / SM) everywhere, 5 = two-Q-tile kernel everywhere
   int attention_impl = 1;
+  int attention_debug = 0;               // timing experiments of the two-Q-tile kernel (attention_tcgen05_pp.cuh), 0 = off
   long long* attention_trace = nullptr;  // device buffer for clock64() stamps (tools/attn_check.py); nullptr in the product
   // bf16 GEMM with N % 256 == 0: 1 = CTA-pair kernel (cta_group::2, 256 x 256 tiles), 0 = single-CTA kernel
   int gemm_pair = 1;
@@ -202,7 +203,15 @@ int ensure_device_setup() {
                                   opv::FaSmemLayout<false>::kTotal));
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   opv::Fa3SmemLayout::kTotal));
-    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_pp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::PpSmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_pp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::PpSmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_pp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::PpSmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_pp_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::PpSmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_pp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   opv::PpSmemLayout::kTotal));
     ds.num_sms = prop.multiProcessorCount;
     ds.attrs_set = true;
@@ -380,8 +389,17 @@ int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, i
       const int64_t total = static_cast<int64_t>(n_seqs) * heads * supers_per_seq;
       if (total > 0x7fffffffLL) return fail(OPV_ERR_UNSUPPORTED, "too many attention tiles for one launch");
       const int grid = static_cast<int>(total < g_num_sms ? total : g_num_sms);
-      launch_pdl(opv::attention_tcgen05_pp_kernel, dim3(grid), dim3(opv::kPpThreads), opv::PpSmemLayout::kTotal, s,
-                 *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, supers_per_seq, pdl_late_flag());
+      auto* kernel = opv::attention_tcgen05_pp_kernel<0>;
+      switch (t_opt.attention_debug) {  // timing experiments of tools/attn_check.py; 0 in the product
+        case 1: kernel = opv::attention_tcgen05_pp_kernel<1>; break;
+        case 2: kernel = opv::attention_tcgen05_pp_kernel<2>; break;
+        case 3: kernel = opv::attention_tcgen05_pp_kernel<3>; break;
+        case 4: kernel = opv::attention_tcgen05_pp_kernel<4>; break;
+        default: break;
+      }
+      launch_pdl(kernel, dim3(grid), dim3(opv::kPpThreads), opv::PpSmemLayout::kTotal, s, *tm_qkv,
+                 static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, supers_per_seq, pdl_late_flag(),
+                 t_opt.attention_trace);
       OPV_LAUNCH_CHECK("attention_tcgen05_pp_kernel");
       return OPV_OK;
     }
@@ -420,6 +438,9 @@ int set_option_in(Options& o, const char* name, int64_t value) {
   if (strcmp(name, "attention_impl") == 0) {
     if (value < 1 || value > 5) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_impl must be 1 .. 5");
     o.attention_impl = static_cast<int>(value);
+  } else if (strcmp(name, "attention_debug") == 0) {
+    if (value < 0 || value > 4) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_debug must be 0 .. 4");
+    o.attention_debug = static_cast<int>(value);
   } else if (strcmp(name, "attention_trace_ptr") == 0) {
     o.attention_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));
   } else if (strcmp(name, "gemm_group_rows") == 0) {

@@ -17,6 +17,8 @@ impl = int(sys.argv[1])
 hw = int(sys.argv[2]) if len(sys.argv) > 2 else -1
 dev = torch.device("cuda:0")
 ops.set_option("attention_impl", impl)
+import os
+dbg = int(os.environ.get("ATTN_DEBUG", "0"))
 
 
 def ref_attention(qkv, lengths, heads, half_window):
@@ -49,6 +51,9 @@ for lengths, heads in (([128], 1), ([256], 1), ([100, 300, 129, 1, 640], 2)):
         print(f"   bad rows {rows} ... bad cols {cols} ...; out[0,:8]={out[0,:8].float().tolist()} ref[0,:8]={ref[0,:8].tolist()}")
 
 # timing at the bench shape: 64 x 2048, 8 heads
+if dbg:
+    ops.set_option("attention_debug", dbg)
+    print(f"attention_debug={dbg}: results below are WRONG by construction, timing only")
 heads, S, B = 8, 2048, 64
 qkv = torch.randn((B * S, 3 * heads * 64), device=dev).to(torch.bfloat16)
 cu = torch.arange(0, B * S + 1, S, dtype=torch.int32, device=dev)
@@ -70,15 +75,31 @@ else:
 print(f"impl={impl} hw={hw} B={B} S={S} heads={heads}: {ms:.3f} ms/launch, {flops / ms / 1e9:.1f} TFLOP/s (algorithmic)", flush=True)
 
 if len(sys.argv) > 3 and sys.argv[3] == "trace":
-    nb = (S + 127) // 128 if hw < 0 else 2
-    buf = torch.zeros(16 * 64, dtype=torch.int64, device=dev)
-    ops.set_option("attention_trace_ptr", buf.data_ptr())
-    ops.attention(qkv, cu, S, heads, hw)
-    torch.cuda.synchronize()
-    ops.set_option("attention_trace_ptr", 0)
-    t = buf.cpu().numpy().reshape(64, 16)[:nb]
-    t0 = t[0, 0]
-    print("block: s_full  S_loaded  max_done  exp_done  pv_done  P_stored | S_issued(i) PV_issued(i) | per softmax warp 0..2: S_loaded, P_stored   (cycles since block 0 s_full)")
-    for i in range(nb):
-        print(f"{i:3d}: " + " ".join(f"{int(v - t0):8d}" if v else "       -" for v in t[i][:14]))
-    print(f"kernel entry {int(t[0][14] - t0)}, exit {int(t[0][15] - t0)} (cycles relative to block 0 s_full)")
+    nb = (S + 127) // 128 if hw < 0 else 3
+    if impl == 5:
+        buf = torch.zeros(32 * 64, dtype=torch.int64, device=dev)
+        ops.set_option("attention_trace_ptr", buf.data_ptr())
+        ops.attention(qkv, cu, S, heads, hw)
+        torch.cuda.synchronize()
+        ops.set_option("attention_trace_ptr", 0)
+        t = buf.cpu().numpy().reshape(64, 32)[:nb]
+        t0 = t[0, 0]
+        print("two-Q-tile kernel, CTA 0, first super tile; cycles since tile A saw s_full(0)")
+        print("blk | A: s_full loaded max_ok exp_done pv_done P_pub | B: s_full loaded max_ok exp_done pv_done P_pub | MMA: S_A S_B PV_A PV_B | TMA: K V")
+        for i in range(nb):
+            def f(v):
+                return f"{int(v - t0):7d}" if v else "      -"
+            print(f"{i:3d} | " + " ".join(f(v) for v in t[i][0:6]) + " | " + " ".join(f(v) for v in t[i][8:14]) + " | "
+                  + " ".join(f(v) for v in t[i][16:20]) + " | " + " ".join(f(v) for v in t[i][24:26]))
+    else:
+        buf = torch.zeros(16 * 64, dtype=torch.int64, device=dev)
+        ops.set_option("attention_trace_ptr", buf.data_ptr())
+        ops.attention(qkv, cu, S, heads, hw)
+        torch.cuda.synchronize()
+        ops.set_option("attention_trace_ptr", 0)
+        t = buf.cpu().numpy().reshape(64, 16)[:nb]
+        t0 = t[0, 0]
+        print("block: s_full  S_loaded  max_done  exp_done  pv_done  P_stored | S_issued(i) PV_issued(i) | per softmax warp 0..2: S_loaded, P_stored   (cycles since block 0 s_full)")
+        for i in range(nb):
+            print(f"{i:3d}: " + " ".join(f"{int(v - t0):8d}" if v else "       -" for v in t[i][:14]))
+        print(f"kernel entry {int(t[0][14] - t0)}, exit {int(t[0][15] - t0)} (cycles relative to block 0 s_full)")
