@@ -27,7 +27,7 @@
 
 namespace opv {
 
-constexpr int kPpThreads = 640;   // warps 0..15 softmax, 16 TMA producer, 17 MMA issuer, 18 TMEM allocation, 19 idle
+constexpr int kPpThreads = 640;   // warps 0..15 softmax, 16 TMA producer, 17 / 18 MMA issuers of tile A / B, 19 TMEM allocation
 constexpr int kPpKvStages = 3;
 constexpr int kPpTmemCols = 512;
 constexpr int kPpSuperM = 2 * kFaBlockM;  // query rows per work unit
@@ -62,25 +62,31 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
   const int heads = H / 64;
   const int total_tiles = n_seqs * heads * supers_per_seq;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + L::kQ;
-  uint8_t* sK = smem + L::kK;
-  uint8_t* sV = smem + L::kV;
-  float* xchg = reinterpret_cast<float*>(smem + L::kExchange);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
-  uint64_t* q_full = bars;             // [2]  Q_j landed                                    (TMA)
-  uint64_t* q_empty = q_full + 2;      // [2]  last S_j of a super tile complete             (tcgen05.commit)
-  uint64_t* k_full = q_empty + 2;      // [S]
-  uint64_t* k_empty = k_full + S;      // [S]  every S MMA reading the stage complete        (tcgen05.commit)
-  uint64_t* v_full = k_empty + S;      // [S]
-  uint64_t* v_empty = v_full + S;      // [S]
-  uint64_t* s_full = v_empty + S;      // [2]  S_j(i) complete in TMEM                       (tcgen05.commit)
-  uint64_t* s_empty = s_full + 2;      // [2]  S_j(i) read into registers                    (8 warp arrivals)
-  uint64_t* p_full = s_empty + 2;      // [2]  P_j(i) written (+ O_j rescaled)               (8 warp arrivals)
-  uint64_t* pv_done = p_full + 2;      // [2]  O_j += P_j(i).V(i) complete                   (tcgen05.commit)
-  uint64_t* o_empty = pv_done + 2;     // [2]  O_j of a super tile read by the epilogue      (8 warp arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024 B alignment (128 B swizzle) is established in the SHARED address space: the shared-window address of a
+  // __shared__ symbol is a compile-time constant, so everything derived from it is free to rematerialise.  Rounding the
+  // GENERIC pointer instead made ptxas rebuild the window base (S2UR SR_SWINHI / SR_CgaCtaId + uniform arithmetic) in
+  // front of every barrier operation of the softmax loop.
+  const uint32_t raw0 = smem_u32(smem_raw);
+  const uint32_t sm0 = (raw0 + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sm0 - raw0);
+  // Every shared-memory address below is the 32-bit shared-window address of the aligned base + a constant, computed
+  // once: the barrier / TMA / descriptor helpers take such addresses (see common.cuh, *_a).
+  const uint32_t a_q = sm0 + L::kQ, a_k = sm0 + L::kK, a_v = sm0 + L::kV, a_xchg = sm0 + L::kExchange;
+  const uint32_t q_full = sm0 + L::kBars;     // [2]  Q_j landed                                    (TMA)
+  const uint32_t q_empty = q_full + 8 * 2;    // [2]  last S_j of a super tile complete             (tcgen05.commit)
+  const uint32_t k_full = q_empty + 8 * 2;    // [S]
+  const uint32_t k_empty = k_full + 8 * S;    // [S]  every S MMA reading the stage complete        (2 x tcgen05.commit)
+  const uint32_t v_full = k_empty + 8 * S;    // [S]
+  const uint32_t v_empty = v_full + 8 * S;    // [S]
+  const uint32_t s_full = v_empty + 8 * S;    // [2]  S_j(i) complete in TMEM                       (tcgen05.commit)
+  const uint32_t s_empty = s_full + 8 * 2;    // [2]  S_j(i) read into registers                    (8 warp arrivals)
+  const uint32_t p_full = s_empty + 8 * 2;    // [2]  P_j(i) written (+ O_j rescaled)               (8 warp arrivals)
+  const uint32_t pv_done = p_full + 8 * 2;    // [2]  O_j += P_j(i).V(i) complete                   (tcgen05.commit)
+  const uint32_t o_empty = pv_done + 8 * 2;   // [2]  O_j of a super tile read by the epilogue      (8 warp arrivals)
+  const uint32_t x_a = o_empty + 8 * 2;       // [4]  per lane quarter: tile B's exponentials issued -> tile A may start
+  const uint32_t x_b = x_a + 8 * 4;           // [4]  per lane quarter: tile A's exponentials issued -> tile B may start
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kBars + 8 * (2 * 7 + 4 * S + 8));
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -125,23 +131,27 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
   if (warp == 16 && lane == 0) tma_prefetch_desc(&tm_qkv);
   if (warp == 17 && lane == 0) {
     for (int j = 0; j < 2; ++j) {
-      mbar_init(&q_full[j], 1);
-      mbar_init(&q_empty[j], 1);
-      mbar_init(&s_full[j], 1);
-      mbar_init(&s_empty[j], 8);
-      mbar_init(&p_full[j], 8);
-      mbar_init(&pv_done[j], 1);
-      mbar_init(&o_empty[j], 8);
+      mbar_init_a(q_full + 8 * j, 1);
+      mbar_init_a(q_empty + 8 * j, 1);
+      mbar_init_a(s_full + 8 * j, 1);
+      mbar_init_a(s_empty + 8 * j, 8);
+      mbar_init_a(p_full + 8 * j, 8);
+      mbar_init_a(pv_done + 8 * j, 1);
+      mbar_init_a(o_empty + 8 * j, 8);
+    }
+    for (int q = 0; q < 4; ++q) {
+      mbar_init_a(x_a + 8 * q, 2);
+      mbar_init_a(x_b + 8 * q, 2);
     }
     for (int s = 0; s < S; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init_a(k_full + 8 * s, 1);
+      mbar_init_a(k_empty + 8 * s, 2);  // one tcgen05.commit per issuer
+      mbar_init_a(v_full + 8 * s, 1);
+      mbar_init_a(v_empty + 8 * s, 2);
     }
     fence_mbar_init();
   }
-  if (warp == 18) {
+  if (warp == 19) {
     tmem_alloc(tmem_slot, kPpTmemCols);
     tmem_relinquish();
   }
@@ -165,9 +175,9 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
           if (!decode(t, st)) continue;
           auto load_q = [&](const int j, uint32_t& td) {
             if (st.hi(j) <= st.lo(j)) return;
-            if (td > 0) mbar_wait(&q_empty[j], (td - 1) & 1);  // the previous super tile's S_j MMAs have read Q_j
-            mbar_expect_tx(&q_full[j], kFaTileBytes);
-            tma_load_2d(sQ + j * kFaTileBytes, &tm_qkv, &q_full[j], st.head * 64, st.begin + st.q0 + j * kFaBlockM);
+            if (td > 0) mbar_wait_a(q_empty + 8 * j, (td - 1) & 1);  // the previous super tile's S_j MMAs have read Q_j
+            mbar_expect_tx_a(q_full + 8 * j, kFaTileBytes);
+            tma_load_2d_a(a_q + j * kFaTileBytes, &tm_qkv, q_full + 8 * j, st.head * 64, st.begin + st.q0 + j * kFaBlockM);
             ++td;
           };
           load_q(0, td0);
@@ -176,18 +186,18 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
           for (int i = 0; i <= st.nb; ++i) {
             if (i < st.nb) {
               const uint32_t sg = kc % S;
-              mbar_wait(&k_empty[sg], ((kc / S) & 1) ^ 1);
-              mbar_expect_tx(&k_full[sg], kFaTileBytes);
-              tma_load_2d(sK + sg * kFaTileBytes, &tm_qkv, &k_full[sg], H + st.head * 64,
+              mbar_wait_a(k_empty + 8 * sg, ((kc / S) & 1) ^ 1);
+              mbar_expect_tx_a(k_full + 8 * sg, kFaTileBytes);
+              tma_load_2d_a(a_k + sg * kFaTileBytes, &tm_qkv, k_full + 8 * sg, H + st.head * 64,
                           st.begin + st.key_base + i * kFaBlockN);
               OPV_PP_STAMP(i, 24);
               ++kc;
             }
             if (i >= 1) {
               const uint32_t sg = vc % S;
-              mbar_wait(&v_empty[sg], ((vc / S) & 1) ^ 1);
-              mbar_expect_tx(&v_full[sg], kFaTileBytes);
-              tma_load_2d(sV + sg * kFaTileBytes, &tm_qkv, &v_full[sg], 2 * H + st.head * 64,
+              mbar_wait_a(v_empty + 8 * sg, ((vc / S) & 1) ^ 1);
+              mbar_expect_tx_a(v_full + 8 * sg, kFaTileBytes);
+              tma_load_2d_a(a_v + sg * kFaTileBytes, &tm_qkv, v_full + 8 * sg, 2 * H + st.head * 64,
                           st.begin + st.key_base + (i - 1) * kFaBlockN);
               OPV_PP_STAMP(i - 1, 25);
               ++vc;
@@ -196,76 +206,76 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
           tracing = false;
         }
       }
-    } else if (warp == 17) {
-      // ------------------------------ MMA issuer --------------------------------
+    } else if ((warp == 17 || warp == 18) && elect_one()) {
+      // ------------------------------ MMA issuers: warp 17 for tile A, warp 18 for tile B (ONE thread each) -------
+      // Everything here is on the critical path of its tile (S_j(i+1) follows s_empty_j(i), P_j(i).V follows
+      // p_full_j(i)).  Every tcgen05.mma / commit / try_wait travels through the scheduler's MIO queue, which the
+      // softmax warps of the same scheduler keep full of MUFU.EX2 (r2 traces: ~130 cycles per dependent trip, a single
+      // issuer needed 3400 cycles for the 24 MMAs + 7 commits + 7 waits of one key block of both tiles).  Hence one
+      // issuer per tile, on two different schedulers, each a single thread with lean waits and nothing in local memory.
+      const int j = warp - 17;
       constexpr uint32_t idesc_s = umma_idesc_bf16_f32(kFaBlockM, kFaBlockN);  // Q.K^T: both K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16_f32_bmn(kFaBlockM, 64);     // P.V: V is MN-major
-      const uint32_t q_addr = smem_u32(sQ);
-      uint32_t td0 = 0, td1 = 0, sc0 = 0, sc1 = 0, pc0 = 0, pc1 = 0, kc = 0, vc = 0;
-      bool tracing_mma = true;
+      const uint32_t q_addr = a_q + j * kFaTileBytes, k_base = a_k, v_base = a_v;
+      const uint32_t t_s = tmem_base + j * 128, t_p = tmem_base + 256 + j * 64, t_o = tmem_base + 384 + j * 64;
+      const uint32_t my_q_full = q_full + 8 * j;
+      const uint32_t my_q_empty = q_empty + 8 * j;
+      const uint32_t my_s_full = s_full + 8 * j;
+      const uint32_t my_s_empty = s_empty + 8 * j;
+      const uint32_t my_p_full = p_full + 8 * j;
+      const uint32_t my_pv_done = pv_done + 8 * j;
+      const uint32_t my_o_empty = o_empty + 8 * j;
+      uint32_t td = 0, sc = 0, pc = 0, kc = 0, vc = 0;
+      bool tracing_mma = trace != nullptr && blockIdx.x == 0;
       Super st;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         if (!decode(t, st)) continue;
+        const int lo = st.lo(j), hi = st.hi(j);
         for (int i = 0; i <= st.nb; ++i) {
-          if (i < st.nb) {  // S_j(i) = Q_j . K(i)^T for the tiles whose range holds block i
+          if (i < st.nb) {  // S_j(i) = Q_j . K(i)^T when this tile's range holds block i
             const uint32_t sg = kc % S;
-            mbar_wait(&k_full[sg], (kc / S) & 1);
-            const uint32_t k_addr = smem_u32(sK + sg * kFaTileBytes);
-            auto issue_s = [&](const int j, const uint32_t td, uint32_t& sc) {
-              if (i < st.lo(j) || i >= st.hi(j)) return;
-              if (i == st.lo(j)) mbar_wait(&q_full[j], td & 1);
-              if (sc > 0) mbar_wait(&s_empty[j], (sc - 1) & 1);  // the softmax warps have read the previous S_j
+            // also when this tile skips the block: the wait keeps this issuer from arriving on k_empty[sg] for the
+            // NEXT use of the stage before the other issuer has arrived for this one (2 arrivals complete a phase)
+            mbar_wait_a(k_full + 8 * sg, (kc / S) & 1);
+            if (i >= lo && i < hi) {
+              const uint32_t k_addr = k_base + sg * kFaTileBytes;
+              if (i == lo) mbar_wait_a(my_q_full, td & 1);
+              if (sc > 0) mbar_wait_a(my_s_empty, (sc - 1) & 1);  // the softmax warps have read the previous S_j
               tc_fence_after();
-              if (elect_one()) {
-                const uint32_t t_s = tmem_base + j * 128;
 #pragma unroll
-                for (int k = 0; k < (DBG == 3 ? 0 : 4); ++k)
-                  umma_bf16_ss(t_s, umma_desc_k_sw128(q_addr + j * kFaTileBytes + k * 32),
-                               umma_desc_k_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
-                umma_commit(&s_full[j]);
-                if (i == st.hi(j) - 1) umma_commit(&q_empty[j]);
-                if (trace != nullptr && blockIdx.x == 0 && tracing_mma) trace[i * 32 + 16 + j] = clock64();
-              }
-              __syncwarp();
+              for (int k = 0; k < (DBG == 3 ? 0 : 4); ++k)
+                umma_bf16_ss(t_s, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32), idesc_s,
+                             k != 0 ? 1u : 0u);
+              umma_commit_a(my_s_full);
+              if (i == hi - 1) umma_commit_a(my_q_empty);
+              if (tracing_mma) trace[i * 32 + 16 + j] = clock64();
               ++sc;
-            };
-            issue_s(0, td0, sc0);
-            issue_s(1, td1, sc1);
-            if (elect_one()) umma_commit(&k_empty[sg]);
-            __syncwarp();
+            }
+            umma_commit_a(k_empty + 8 * sg);  // both issuers arrive for every block, whether their tile used it or not
             ++kc;
           }
           if (i >= 1) {  // O_j += P_j(b) . V(b)
             const int b = i - 1;
             const uint32_t sg = vc % S;
-            mbar_wait(&v_full[sg], (vc / S) & 1);
-            const uint32_t v_addr = smem_u32(sV + sg * kFaTileBytes);
-            auto issue_pv = [&](const int j, const uint32_t td, uint32_t& pc) {
-              if (b < st.lo(j) || b >= st.hi(j)) return;
-              mbar_wait(&p_full[j], pc & 1);
-              if (b == st.lo(j) && td > 0) mbar_wait(&o_empty[j], (td - 1) & 1);  // epilogue has read the previous O_j
+            mbar_wait_a(v_full + 8 * sg, (vc / S) & 1);
+            if (b >= lo && b < hi) {
+              const uint32_t v_addr = v_base + sg * kFaTileBytes;
+              mbar_wait_a(my_p_full, pc & 1);
+              if (b == lo && td > 0) mbar_wait_a(my_o_empty, (td - 1) & 1);  // epilogue has read the previous O_j
               tc_fence_after();
-              if (elect_one()) {
-                const uint32_t t_p = tmem_base + 256 + j * 64, t_o = tmem_base + 384 + j * 64;
-                const uint32_t first = b == st.lo(j) ? 0u : 1u;
+              const uint32_t first = b == lo ? 0u : 1u;
 #pragma unroll
-                for (int k = 0; k < (DBG == 3 ? 0 : 8); ++k)  // 16 keys per MMA: two 8-key groups of 1024 B
-                  umma_bf16_ts(t_o, t_p + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_o, (k != 0) ? 1u : first);
-                umma_commit(&pv_done[j]);
-                if (trace != nullptr && blockIdx.x == 0 && tracing_mma) trace[b * 32 + 18 + j] = clock64();
-              }
-              __syncwarp();
+              for (int k = 0; k < (DBG == 3 ? 0 : 8); ++k)  // 16 keys per MMA: two 8-key groups of 1024 B
+                umma_bf16_ts(t_o, t_p + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_o, (k != 0) ? 1u : first);
+              umma_commit_a(my_pv_done);
+              if (tracing_mma) trace[b * 32 + 18 + j] = clock64();
               ++pc;
-            };
-            issue_pv(0, td0, pc0);
-            issue_pv(1, td1, pc1);
-            if (elect_one()) umma_commit(&v_empty[sg]);
-            __syncwarp();
+            }
+            umma_commit_a(v_empty + 8 * sg);
             ++vc;
           }
         }
-        if (st.hi0 > st.lo0) ++td0;
-        if (st.hi1 > st.lo1) ++td1;
+        if (hi > lo) ++td;
         tracing_mma = false;
       }
     }
@@ -276,19 +286,23 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
     const int r_tile = quarter * 32 + lane;  // row inside the tile == TMEM lane
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t t_s = lane_base + j * 128 + 64 * half;        // this thread's 64 score columns
+    const uint32_t t_other = lane_base + j * 128 + 64 * (half ^ 1);  // the other half's (row max only)
     const uint32_t t_p = lane_base + 256 + j * 64 + 32 * half;   // its 32 packed-probability columns
     const uint32_t t_o = lane_base + 384 + j * 64 + 32 * half;   // the 32 output columns it rescales / stores
     const float scale_log2 = 0.125f * 1.44269504088896340736f;   // head_dim^-0.5 * log2(e)
     const int pair_bar = 1 + j * 4 + quarter;                    // named barrier of the two warps sharing these rows
     // row max / row sum exchange between the two halves of a row; slots alternate with the block parity so that a
     // thread that runs ahead cannot overwrite a value its partner has not read yet
-    float* const my_slots = xchg + j * 512 + half * 128 + r_tile;
-    const float* const other_slots = xchg + j * 512 + (half ^ 1) * 128 + r_tile;
-    uint64_t* const my_s_full = &s_full[j];
-    uint64_t* const my_s_empty = &s_empty[j];
-    uint64_t* const my_p_full = &p_full[j];
-    uint64_t* const my_pv_done = &pv_done[j];
-    uint64_t* const my_o_empty = &o_empty[j];
+    const uint32_t my_slots = a_xchg + 4 * (j * 512 + half * 128 + r_tile);        // + 1024 B for the odd parity
+    const uint32_t other_slots = a_xchg + 4 * (j * 512 + (half ^ 1) * 128 + r_tile);
+    const uint32_t tok_wait = j == 0 ? x_a + 8 * quarter : x_b + 8 * quarter;   // exponential-phase token (see below)
+    const uint32_t tok_pass = j == 0 ? x_b + 8 * quarter : x_a + 8 * quarter;
+    uint32_t tok = 0;  // token phases consumed by this tile
+    const uint32_t my_s_full = s_full + 8 * j;
+    const uint32_t my_s_empty = s_empty + 8 * j;
+    const uint32_t my_p_full = p_full + 8 * j;
+    const uint32_t my_pv_done = pv_done + 8 * j;
+    const uint32_t my_o_empty = o_empty + 8 * j;
     uint32_t bc = 0;  // running count of this tile's key blocks -> barrier parity
     tracing = tracing && half == 0 && quarter == 0;
     const int tslot = 8 * j;
@@ -297,6 +311,7 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
       if (!decode(t, st)) continue;
       const int lo = st.lo(j), hi = st.hi(j);
       if (hi <= lo) continue;  // second tile of a super tile that ends inside the first one
+      const bool use_token = DBG == 0 && global && st.hi1 > st.lo1;  // both tiles walk the same key blocks
       const int n = st.n, q0 = st.q0 + j * kFaBlockM;
       const int row = q0 + r_tile;  // row inside the sequence
       float m_run = -CUDART_INF_F, l_run = 0.f;
@@ -312,116 +327,103 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
       const int any_hi = global ? n - 1 : min(row_last + half_window, n - 1);
 
       for (int i = lo; i < hi; ++i, ++bc) {
-        const int key0 = st.key_base + i * kFaBlockN + 64 * half;  // first key of this thread's 64
-        int kind[2];  // per 32-key chunk, warp-uniform: 0 = no row sees it, 1 = every row sees all of it, 2 = mixed
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int c_lo = key0 + 32 * q, c_hi = c_lo + 31;
-          kind[q] = (c_hi < any_lo || c_lo > any_hi) ? 0 : ((c_lo >= all_lo && c_hi <= all_hi) ? 1 : 2);
+        const int blk_key0 = st.key_base + i * kFaBlockN;
+        // the block's four 32-key chunks, warp-uniform and the same in both halves of a row pair:
+        // 0 = no row of this warp sees it, 1 = every row sees all of it, 2 = mixed
+        auto kind_of = [&](const int q) {  // arithmetic only: an indexable array would live in local memory
+          const int c_lo = blk_key0 + 32 * q, c_hi = c_lo + 31;
+          return (c_hi < any_lo || c_lo > any_hi) ? 0 : ((c_lo >= all_lo && c_hi <= all_hi) ? 1 : 2);
+        };
+        const int own = 2 * half, oth = 2 * (half ^ 1);
+        int k_own0 = 1, k_own1 = 1, k_oth0 = 1, k_oth1 = 1;
+        // global layers: every block but a sequence's last one is fully visible -- one compare instead of four chunk
+        // classifications (this loop is instruction-issue bound: ~480 instructions per 64 scores before this was trimmed)
+        bool all_full = global && blk_key0 + kFaBlockN <= n;
+        if (!all_full) {
+          k_own0 = kind_of(own), k_own1 = kind_of(own + 1), k_oth0 = kind_of(oth), k_oth1 = kind_of(oth + 1);
+          all_full = (k_own0 & k_own1 & k_oth0 & k_oth1) == 1;
         }
-        mbar_wait(my_s_full, bc & 1);
+        const int key0 = blk_key0 + 64 * half;  // first key of this thread's 64
+        // -inf for the keys of a 32-column chunk starting at key `first` that this row does not see
+        auto mask32 = [&](uint32_t* v, const int first) {
+          const int d = first - k_lo;
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (static_cast<uint32_t>(d + c) > k_span) v[c] = 0xff800000u;
+        };
+        auto max32 = [&](const uint32_t* v, float& a, float& b) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            a = fmax3(a, __uint_as_float(v[c + 0]), __uint_as_float(v[c + 1]));
+            b = fmax3(b, __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+          }
+        };
+
+        mbar_wait_a(my_s_full, bc & 1);
         tc_fence_after();
         OPV_PP_STAMP(i, tslot + 0);
-        uint32_t sr[64];
+        // ---- scores: this thread's 64 columns stay in registers; the OTHER half's 64 are only read for the row max,
+        // 32 at a time.  Both threads of a row thus compute the same full-row max on their own: no exchange through
+        // shared memory and no pair barrier on the per-block path (three dependent trips through the MIO queue, each
+        // ~130 cycles while the other tile's MUFU.EX2 stream keeps that queue full -- r2 trace).
+        uint32_t sr[64], ot[32];
         if constexpr (DBG == 2) {
 #pragma unroll
           for (int c = 0; c < 64; ++c) sr[c] = __float_as_uint(static_cast<float>((lane * 7 + c * 3 + i) & 31) * 0.01f);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) ot[c] = sr[c];
         } else {
-          tmem_ld_32x32b_x64(t_s, sr);
+          tmem_ld_32x32b_x64_nowait(t_s, sr);
+          tmem_ld_32x32b_x32_nowait(t_other, ot);
+          tmem_wait_ld_fence64(sr);
+          tmem_ld_fence32(ot);
         }
         OPV_PP_STAMP(i, tslot + 1);
+        float mo0 = -CUDART_INF_F, mo1 = -CUDART_INF_F;
+        if (all_full) {
+          max32(ot, mo0, mo1);
+        } else if (k_oth0 != 0) {
+          if (k_oth0 == 2) mask32(ot, blk_key0 + 32 * oth);
+          max32(ot, mo0, mo1);
+        }
+        if constexpr (DBG != 2) tmem_ld_32x32b_x32_nowait(t_other + 32, ot);  // in flight under the own-half max
+        float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+        if (all_full) {
+          max32(sr, mx0, mx1);
+          max32(sr + 32, mx0, mx1);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int kq = q ? k_own1 : k_own0;
+            if (kq == 0) continue;
+            if (kq == 2) mask32(sr + 32 * q, key0 + 32 * q);
+            max32(sr + 32 * q, mx0, mx1);
+          }
+        }
+        if constexpr (DBG != 2) tmem_wait_ld_fence32(ot);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(my_s_empty);  // the MMA warp may overwrite S_j with S_j(i+1)
-
-        uint32_t pr[32];
-        float corr, sum;
-        bool upd;
-        if (kind[0] == 1 && kind[1] == 1) {
-          // Every block of a global layer except a sequence's last one: ONE straight-line basic block.
-          float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
-#pragma unroll
-          for (int c = 0; c < 64; c += 8) {
-            mx0 = fmax3(mx0, __uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1]));
-            mx1 = fmax3(mx1, __uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
-            mx2 = fmax3(mx2, __uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5]));
-            mx3 = fmax3(mx3, __uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7]));
-          }
-          const float mine = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-          float mx = mine;
-          if constexpr (DBG != 4) {
-            my_slots[(bc & 1) * 256] = mine;
-            named_bar_sync(pair_bar, 64);
-            mx = fmaxf(mine, other_slots[(bc & 1) * 256]);
-          }
-          OPV_PP_STAMP_F(i, tslot + 2, mx);
-          const float m_cand = fmaxf(m_run, mx * scale_log2);  // finite
-          upd = (m_cand - m_run) > kFaRescaleThreshold;
-          const float m_new = upd ? m_cand : m_run;
-          corr = upd ? ex2_approx(m_run - m_new) : 1.0f;
-          m_run = m_new;
-          float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const float a = ex2(fmaf(__uint_as_float(sr[2 * c]), scale_log2, -m_new));
-            const float b = ex2(fmaf(__uint_as_float(sr[2 * c + 1]), scale_log2, -m_new));
-            const float e = ex2(fmaf(__uint_as_float(sr[2 * c + 2]), scale_log2, -m_new));
-            const float f = ex2(fmaf(__uint_as_float(sr[2 * c + 3]), scale_log2, -m_new));
-            sum0 += a, sum1 += b, sum2 += e, sum3 += f;
-            pr[c] = pack_bf16x2(a, b);
-            pr[c + 1] = pack_bf16x2(e, f);
-          }
-          sum = (sum0 + sum1) + (sum2 + sum3);
-        } else {
-          float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            if (kind[q] == 0) continue;
-            if (kind[q] == 2) {
-              const int d = key0 + 32 * q - k_lo;
-#pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if (static_cast<uint32_t>(d + c) > k_span) sr[32 * q + c] = 0xff800000u;  // -inf
-            }
-#pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              mx0 = fmax3(mx0, __uint_as_float(sr[32 * q + c + 0]), __uint_as_float(sr[32 * q + c + 1]));
-              mx1 = fmax3(mx1, __uint_as_float(sr[32 * q + c + 2]), __uint_as_float(sr[32 * q + c + 3]));
-            }
-          }
-          const float mine = fmaxf(mx0, mx1);
-          my_slots[(bc & 1) * 256] = mine;
-          named_bar_sync(pair_bar, 64);
-          const float mx = fmaxf(mine, other_slots[(bc & 1) * 256]);
-          const float m_cand = fmaxf(m_run, mx * scale_log2);
-          upd = (m_cand - m_run) > kFaRescaleThreshold;  // false when both are -inf (NaN); same in both halves
-          const float m_new = upd ? m_cand : m_run;
-          corr = upd ? ex2_approx(m_run - m_new) : 1.0f;
-          const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-          m_run = m_new;
-          float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            if (kind[q] == 0) {
-#pragma unroll
-              for (int c = 0; c < 16; ++c) pr[16 * q + c] = 0u;
-            } else {
-#pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                const float a = ex2(fmaf(__uint_as_float(sr[32 * q + 2 * c]), scale_log2, -m_use));
-                const float b = ex2(fmaf(__uint_as_float(sr[32 * q + 2 * c + 1]), scale_log2, -m_use));
-                sum0 += a, sum1 += b;
-                pr[16 * q + c] = pack_bf16x2(a, b);
-              }
-            }
-          }
-          sum = sum0 + sum1;
+        if (lane == 0) mbar_arrive_a(my_s_empty);  // the MMA warp may overwrite S_j with S_j(i+1)
+        if (all_full) {
+          max32(ot, mo0, mo1);
+        } else if (k_oth1 != 0) {
+          if (k_oth1 == 2) mask32(ot, blk_key0 + 32 * (oth + 1));
+          max32(ot, mo0, mo1);
         }
-        OPV_PP_STAMP_F(i, tslot + 3, sum);
-        l_run = l_run * corr + sum;
+        float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mo0, mo1));
+        OPV_PP_STAMP_F(i, tslot + 2, mx);
+        const float m_cand = fmaxf(m_run, mx * scale_log2);
+        const bool upd = (m_cand - m_run) > kFaRescaleThreshold;  // false when both are -inf (NaN); same in both halves
+        const float m_new = upd ? m_cand : m_run;
+        const float corr = upd ? ex2_approx(m_run - m_new) : 1.0f;
+        const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
+        m_run = m_new;
 
+        // ---- O_j holds blocks < i and the P_j buffer is free again; lazy rescale of this thread's 32 output columns.
+        // Done BEFORE the exponentials: this wait and the TMEM round trip then sit in the shadow of the other tile's
+        // exponential phase instead of between this tile's last MUFU and its p_full.
         if (i > lo) {
-          mbar_wait(my_pv_done, (bc - 1) & 1);  // O_j holds blocks < i and the P_j buffer is free again
+          mbar_wait_a(my_pv_done, (bc - 1) & 1);
           tc_fence_after();
           OPV_PP_STAMP(i, tslot + 4);
           if (__any_sync(0xffffffffu, upd)) {
@@ -432,25 +434,78 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
             tmem_st_32x32b_x32(t_o, orr);
           }
         }
-        tmem_st_32x32b_x32(t_p, pr);
+
+        // ---- exponential-phase token.  MUFU.EX2 (16 / clk / SM) bounds this kernel, and the four softmax warps of a
+        // scheduler otherwise drift into phase: all of them issue exponentials at once (each at a quarter of the
+        // rate), then all of them sit in TMEM round trips and barrier hand-offs with the unit idle (r2 trace: 1800
+        // cycles of exponentials + 1250 of everything else per block, XU 62 % busy).  With both tiles walking the same
+        // key blocks, tile B starts its exponentials of block i when tile A has issued (most of) its own, and tile A
+        // those of block i+1 when B is through with block i: one tile's loads, row max, hand-offs and stores run under
+        // the other tile's exponentials.  Per lane quarter (= per scheduler), 2 warp arrivals per phase.
+        if (use_token && (j == 1 || i > lo)) {
+          mbar_wait_a(tok_wait, tok & 1);
+          ++tok;
+        }
+        // Packed fp32 pairs (FFMA2 / FADD2, new on sm_100): the scale-and-shift and the row-sum accumulation cost half
+        // an issue slot per score instead of one each.  This loop is co-limited by MUFU.EX2 and by issue slots (r2
+        // profile: 57 % issue utilisation, 62 % XU), so instructions per score are the lever.
+        float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
+        const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-m_use, -m_use);
+        auto exp8 = [&](uint32_t* pq, const int q, const int c0) {  // 16 scores -> 8 packed probability pairs
+#pragma unroll
+          for (int c = c0; c < c0 + 8; c += 2) {
+            const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(sr[32 * q + 2 * c]), __uint_as_float(sr[32 * q + 2 * c + 1])), sc2, nm2);
+            const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(sr[32 * q + 2 * c + 2]), __uint_as_float(sr[32 * q + 2 * c + 3])), sc2, nm2);
+            const float2 p01 = make_float2(ex2(x01.x), ex2(x01.y));
+            const float2 p23 = make_float2(ex2(x23.x), ex2(x23.y));
+            acc01 = __fadd2_rn(acc01, p01);
+            acc23 = __fadd2_rn(acc23, p23);
+            pq[c] = pack_bf16x2(p01.x, p01.y);
+            pq[c + 1] = pack_bf16x2(p23.x, p23.y);
+          }
+        };
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t pq[16];
+          const bool skip = !all_full && (q ? k_own1 : k_own0) == 0;  // no row of this warp sees these 32 keys
+          if (skip) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pq[c] = 0u;
+          } else {
+            exp8(pq, q, 0);
+          }
+          if (q == 1 && use_token && (j == 0 || i + 1 < hi)) {
+            // three quarters of this block's exponentials are issued: hand the token over now, so that the other
+            // tile's wake-up overlaps the tail (tile B's last block of a super tile has no successor to release)
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(tok_pass);
+          }
+          if (!skip) exp8(pq, q, 8);
+          tmem_st_32x32b_x16_nowait(t_p + 16 * q, pq);  // drains under the remaining exponentials
+        }
+        const float2 acc = __fadd2_rn(acc01, acc23);
+        float sum = acc.x + acc.y;
+        OPV_PP_STAMP_F(i, tslot + 3, sum);
+        l_run = l_run * corr + sum;
+        tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(my_p_full);
+        if (lane == 0) mbar_arrive_a(my_p_full);
         OPV_PP_STAMP(i, tslot + 5);
       }
       tracing = false;
 
       // epilogue: O / l -> bf16 -> out[begin + row, head*64 + 32*half : +32]
-      my_slots[(bc & 1) * 256] = l_run;  // parity of the NEXT block: last used two blocks ago
-      mbar_wait(my_pv_done, (bc - 1) & 1);
+      st_shared_f32(my_slots + (bc & 1) * 1024, l_run);  // parity of the NEXT block: last used two blocks ago
+      mbar_wait_a(my_pv_done, (bc - 1) & 1);
       tc_fence_after();
       uint32_t orr[32];
       tmem_ld_32x32_raw(t_o, orr);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(my_o_empty);  // the next super tile's first P_j.V may overwrite O_j
+      if (lane == 0) mbar_arrive_a(my_o_empty);  // the next super tile's first P_j.V may overwrite O_j
       named_bar_sync(pair_bar, 64);
-      const float l_total = l_run + other_slots[(bc & 1) * 256];
+      const float l_total = l_run + ld_shared_f32(other_slots + (bc & 1) * 1024);
       named_bar_sync(pair_bar, 64);  // both halves have read the sums before the next tile's max exchange
       if (row < n) {
         const float inv = 1.0f / l_total;
@@ -470,7 +525,7 @@ attention_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 18) tmem_dealloc(tmem_base, kPpTmemCols);
+  if (warp == 19) tmem_dealloc(tmem_base, kPpTmemCols);
 #undef OPV_PP_STAMP
 #undef OPV_PP_STAMP_F
 }

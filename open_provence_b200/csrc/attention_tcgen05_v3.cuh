@@ -40,8 +40,12 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
   const int heads = H / 64;
   const int total_tiles = n_seqs * heads * tiles_per_seq;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024 B alignment (128 B swizzle) established in the SHARED address space: the shared-window address of a __shared__
+  // symbol is a compile-time constant.  Rounding the GENERIC pointer made ptxas rebuild the window base (S2UR
+  // SR_SWINHI / SR_CgaCtaId + uniform arithmetic) in front of every barrier operation (profiles/r2_attention_notes.md).
+  const uint32_t raw0 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw0 + 1023u) & ~1023u) - raw0);
   uint8_t* sQ = smem + L::kQ;
   uint8_t* sK = smem + L::kK;
   uint8_t* sV = smem + L::kV;
@@ -117,13 +121,13 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
       Tile tl;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         if (!decode(t, tl)) continue;
-        if (tiles_done > 0) mbar_wait(q_empty, (tiles_done - 1) & 1);
+        if (tiles_done > 0) mbar_wait_spin(q_empty, (tiles_done - 1) & 1);
         mbar_expect_tx(q_full, kFaTileBytes);
         tma_load_2d(sQ, &tm_qkv, q_full, tl.head * 64, tl.begin + tl.q0);
         for (int i = 0; i <= tl.nb; ++i) {  // consumption order of the MMA warp: K0, K1, V0, K2, V1, ...
           if (i < tl.nb) {
             const uint32_t st = kc % kFaKvStages;
-            mbar_wait(&k_empty[st], ((kc / kFaKvStages) & 1) ^ 1);
+            mbar_wait_spin(&k_empty[st], ((kc / kFaKvStages) & 1) ^ 1);
             mbar_expect_tx(&k_full[st], kFaTileBytes);
             tma_load_2d(sK + st * kFaTileBytes, &tm_qkv, &k_full[st], H + tl.head * 64,
                         tl.begin + tl.key_base + i * kFaBlockN);
@@ -131,7 +135,7 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
           }
           if (i >= 1) {
             const uint32_t st = vc % kFaKvStages;
-            mbar_wait(&v_empty[st], ((vc / kFaKvStages) & 1) ^ 1);
+            mbar_wait_spin(&v_empty[st], ((vc / kFaKvStages) & 1) ^ 1);
             mbar_expect_tx(&v_full[st], kFaTileBytes);
             tma_load_2d(sV + st * kFaTileBytes, &tm_qkv, &v_full[st], 2 * H + tl.head * 64,
                         tl.begin + tl.key_base + (i - 1) * kFaBlockN);
@@ -150,8 +154,8 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
     uint32_t tiles_done = 0, sc = 0, pc = 0;
     auto issue_s = [&](const bool last_of_tile) {  // S = Q . K^T for the next key block
       const uint32_t st = sc % kFaKvStages;
-      mbar_wait(&k_full[st], (sc / kFaKvStages) & 1);
-      if (sc > 0) mbar_wait(s_empty, (sc - 1) & 1);
+      mbar_wait_spin(&k_full[st], (sc / kFaKvStages) & 1);
+      if (sc > 0) mbar_wait_spin(s_empty, (sc - 1) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t k_addr = smem_u32(sK + st * kFaTileBytes);
@@ -169,14 +173,14 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
     Tile tl;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       if (!decode(t, tl)) continue;
-      mbar_wait(q_full, tiles_done & 1);
+      mbar_wait_spin(q_full, tiles_done & 1);
       issue_s(tl.nb == 1);
       for (int i = 0; i < tl.nb; ++i) {
         if (i + 1 < tl.nb) issue_s(i + 2 == tl.nb);
         const uint32_t st = pc % kFaKvStages;
-        mbar_wait(&v_full[st], (pc / kFaKvStages) & 1);
-        mbar_wait(p_full, pc & 1);
-        if (i == 0 && tiles_done > 0) mbar_wait(o_empty, (tiles_done - 1) & 1);
+        mbar_wait_spin(&v_full[st], (pc / kFaKvStages) & 1);
+        mbar_wait_spin(p_full, pc & 1);
+        if (i == 0 && tiles_done > 0) mbar_wait_spin(o_empty, (tiles_done - 1) & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t v_addr = smem_u32(sV + st * kFaTileBytes);
@@ -231,7 +235,7 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
           const int c_lo = key0 + 32 * q, c_hi = c_lo + 31;
           kind[q] = (c_hi < any_lo || c_lo > any_hi) ? 0 : ((c_lo >= all_lo && c_hi <= all_hi) ? 1 : 2);
         }
-        mbar_wait(s_full, bc & 1);
+        mbar_wait_spin(s_full, bc & 1);
         tc_fence_after();
 
         // ---- pass 1: row max over this thread's 64 scores
@@ -264,7 +268,7 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
         m_run = m_new;
 
         if (i > 0) {
-          mbar_wait(pv_done, (bc - 1) & 1);  // O holds blocks < i and the P buffer is free again
+          mbar_wait_spin(pv_done, (bc - 1) & 1);  // O holds blocks < i and the P buffer is free again
           tc_fence_after();
           if (__any_sync(0xffffffffu, upd)) {
             uint32_t orr[32];
@@ -276,7 +280,9 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
         }
 
         // ---- pass 2: exponentials, 32 keys at a time; the packed probabilities leave in 16-column stores
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+        // packed fp32 pairs (FFMA2 / FADD2, sm_100): half an issue slot per score for scale-and-shift and row sum
+        float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
+        const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-m_use, -m_use);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           uint32_t pq[16];
@@ -294,13 +300,14 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
             }
 #pragma unroll
             for (int c = 0; c < 16; c += 2) {
-              const float a = ex2_approx(fmaf(__uint_as_float(sr[2 * c]), scale_log2, -m_use));
-              const float b = ex2_approx(fmaf(__uint_as_float(sr[2 * c + 1]), scale_log2, -m_use));
-              const float e = ex2_approx(fmaf(__uint_as_float(sr[2 * c + 2]), scale_log2, -m_use));
-              const float f = ex2_approx(fmaf(__uint_as_float(sr[2 * c + 3]), scale_log2, -m_use));
-              sum0 += a, sum1 += b, sum2 += e, sum3 += f;
-              pq[c] = pack_bf16x2(a, b);
-              pq[c + 1] = pack_bf16x2(e, f);
+              const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1])), sc2, nm2);
+              const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(sr[2 * c + 2]), __uint_as_float(sr[2 * c + 3])), sc2, nm2);
+              const float2 p01 = make_float2(ex2_approx(x01.x), ex2_approx(x01.y));
+              const float2 p23 = make_float2(ex2_approx(x23.x), ex2_approx(x23.y));
+              acc01 = __fadd2_rn(acc01, p01);
+              acc23 = __fadd2_rn(acc23, p23);
+              pq[c] = pack_bf16x2(p01.x, p01.y);
+              pq[c + 1] = pack_bf16x2(p23.x, p23.y);
             }
           }
           tmem_st_32x32b_x16_nowait(t_p + 16 * q, pq);
@@ -309,7 +316,8 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);
-        l_run = l_run * corr + ((sum0 + sum1) + (sum2 + sum3));
+        const float2 acc = __fadd2_rn(acc01, acc23);
+        l_run = l_run * corr + (acc.x + acc.y);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -318,7 +326,7 @@ attention_tcgen05_v3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
 
       // epilogue: O / l -> bf16 -> out[begin + row, head*64 + 32*half : +32]
       my_slots[(bc & 1) * 256] = l_run;  // parity of the NEXT block: last used two blocks ago
-      mbar_wait(pv_done, (bc - 1) & 1);
+      mbar_wait_spin(pv_done, (bc - 1) & 1);
       tc_fence_after();
       uint32_t orr[32];
       tmem_ld_32x32_raw(t_o, orr);

@@ -148,6 +148,55 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Lean bounded wait for the hot loops of the single-thread producer / issuer roles and the softmax warps: no clock64,
+// no printf (the call ABI of the message costs registers and a stack frame in every caller -- in a 32-register MMA
+// issuer that meant local-memory traffic on the critical path).  Each failed try_wait may suspend the thread for up to
+// the 10 ms hint, so 1024 of them bound a hung protocol to seconds; then the kernel traps (the host sees an error).
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t tries = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++tries > 1024u) __trap();
+  }
+}
+// The same primitives on 32-bit shared-window addresses computed ONCE per kernel (smem_u32 of the barrier block +
+// constant offsets).  Passing generic pointers makes the compiler re-derive the shared window (S2UR SR_SWINHI /
+// SR_CgaCtaId + uniform arithmetic, ~10 dependent instructions) in front of every barrier operation.
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t tries = 0;
+  while (!mbar_try_wait_a(bar, parity)) {
+    if (++tries > 1024u) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 // Programmatic dependent launch (PDL).  A kernel launched with programmaticStreamSerializationAllowed may become
 // resident while its predecessor in the stream is still running; pdl_wait() blocks until every prerequisite grid has
 // completed and its memory is visible, so everything before it (barrier init, TMEM allocation, descriptor prefetch)
@@ -297,6 +346,18 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int32_t c0,
+                                              int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
 }
 
 // TMEM -> registers: 32 lanes x 32 consecutive fp32 columns; thread i of the warp receives lane

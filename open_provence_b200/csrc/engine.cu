@@ -100,9 +100,9 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 // defaults at call time.  Nothing below reads a process-global while launching: each extern "C" entry point copies
 // the options of ITS engine (or the defaults) and the SM count of the CURRENT device into thread-local state.
 struct Options {
-  // bf16 attention kernel: 1 = default (two-Q-tile kernel for global layers, two-threads-per-row kernel for
+  // bf16 attention kernel: 1 = default (one-thread-per-row kernel for global layers, two-threads-per-row kernel for
   // sliding-window layers), 2 = one-thread-per-row with P in smem, 3 = two-threads-per-row everywhere,
-  // 4 = one-thread-per-row (P in TMEM, 2 CTAs / SM) everywhere, 5 = two-Q-tile kernel everywhere
+  // 4 = one-thread-per-row (P in TMEM, 2 CTAs / SM) everywhere, 5 = two-Q-tile kernel (1 CTA / SM) everywhere
   int attention_impl = 1;
   int attention_debug = 0;               // timing experiments of the two-Q-tile kernel (attention_tcgen05_pp.cuh), 0 = off
   long long* attention_trace = nullptr;  // device buffer for clock64() stamps (tools/attn_check.py); nullptr in the product
@@ -383,7 +383,7 @@ int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, i
   if (dtype == OPV_DTYPE_BF16) {
     if (!tm_qkv) return fail(OPV_ERR_INVALID_ARGUMENT, "tcgen05 attention needs the qkv tensor map");
     const int impl = t_opt.attention_impl;
-    if (impl == 5 || (impl == 1 && half_window < 0)) {
+    if (impl == 5) {
       // persistent, ONE CTA per SM: (sequence, head, 256-query super tile) list with a grid stride, two Q tiles in flight
       const int supers_per_seq = (max_seqlen + opv::kPpSuperM - 1) / opv::kPpSuperM;
       const int64_t total = static_cast<int64_t>(n_seqs) * heads * supers_per_seq;
@@ -410,11 +410,11 @@ int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, i
     const int grid = static_cast<int>(total_tiles < 2 * g_num_sms ? total_tiles : 2 * g_num_sms);
     // sliding-window layers: two softmax threads per row (0.156 vs 0.176 ms per layer at 64 x 2048); 3 / 4 force one
     // of the 2-CTAs-per-SM kernels everywhere
-    if (impl == 3 || impl == 1)
+    if (impl == 3 || (impl == 1 && half_window >= 0))
       launch_pdl(opv::attention_tcgen05_v3_kernel, dim3(grid), dim3(opv::kFa3Threads), opv::Fa3SmemLayout::kTotal, s,
                  *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq,
                  pdl_late_flag());
-    else if (impl == 4)
+    else if (impl == 4 || impl == 1)
       launch_pdl(opv::attention_tcgen05_kernel<true>, dim3(grid), dim3(opv::kFaThreads), opv::FaSmemLayout<true>::kTotal,
                  s, *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq,
                  t_opt.attention_trace, pdl_late_flag());

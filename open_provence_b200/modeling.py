@@ -178,6 +178,8 @@ class OpenProvenceModel:
         dtype: Any = None,
         fuse_epilogues: bool = True,
         scorer: Any = None,
+        process_group: Any = None,
+        data_parallel: bool = False,
     ) -> None:
         self.config = config
         self.max_length = int(config.max_length)
@@ -208,12 +210,35 @@ class OpenProvenceModel:
                 fuse_epilogues=fuse_epilogues,
             )
             self._runtime_device = self.engine.device
-            self._scorer = DeviceScorer(self.engine)
+            if scorer is None:  # an injected scorer (tests, custom sharding) is kept
+                self._scorer = DeviceScorer(self.engine)
+            if data_parallel or process_group is not None:
+                self.enable_data_parallel(process_group)
         else:
             self._runtime_device = torch.device("cpu")
         if tokenizer is not None:
             self._update_tokenizer_runtime()
             self._update_runtime_defaults()
+
+    # ------------------------------------------------------------------ multi-GPU
+    def enable_data_parallel(self, process_group: Any = None) -> "OpenProvenceModel":
+        """Shard the blocks of every ``process()`` call over the ranks of ``process_group`` (default: the world
+        group of an initialised ``torch.distributed``; one process per GPU, NCCL).  Weights stay replicated; every
+        rank must call ``process()`` with the same arguments and receives the same, complete result.  One
+        all-gather of ``[rank scores | fragment means]`` per call (``sharding.ShardedScorer``)."""
+        import torch.distributed as dist
+
+        from .sharding import ShardedScorer
+
+        if not dist.is_available() or not dist.is_initialized():
+            raise RuntimeError("enable_data_parallel() needs an initialised torch.distributed process group")
+        if isinstance(self._scorer, ShardedScorer):
+            self._scorer.group = process_group
+            return self
+        base = self.config.base_model_config or {}
+        self._scorer = ShardedScorer(self._scorer, process_group, hidden=int(base.get("hidden_size", 512)),
+                                     inter=int(base.get("intermediate_size", 2048)))
+        return self
 
     # ------------------------------------------------------------------ loading
     @classmethod
@@ -245,6 +270,8 @@ class OpenProvenceModel:
             dtype = torch.bfloat16
         kwargs.pop("attn_implementation", None)
         fuse = bool(kwargs.pop("fuse_epilogues", True))
+        process_group = kwargs.pop("process_group", None)
+        data_parallel = bool(kwargs.pop("data_parallel", False))
 
         path = Path(pretrained_model_name_or_path)
         if not path.is_dir():
@@ -260,7 +287,8 @@ class OpenProvenceModel:
         config = OpenProvenceConfig.from_pretrained(path)
         state = _load_state_dict(path)
         tokenizer = cls._init_tokenizer(config, path)
-        model = cls(config, state, tokenizer, device=resolved_device, dtype=dtype, fuse_epilogues=fuse)
+        model = cls(config, state, tokenizer, device=resolved_device, dtype=dtype, fuse_epilogues=fuse,
+                    process_group=process_group, data_parallel=data_parallel)
         if max_length is not None:
             model.max_length = int(max_length)
             model.config.max_length = int(max_length)
@@ -909,6 +937,8 @@ class OpenProvenceModel:
             self._scorer.max_tokens = max(131072, batch_size * max(self.max_length, 1))
         plans: list[_ContextPlan] = []
         parts: list[dict[str, np.ndarray]] = []
+        tickets: list[Any] = []
+        two_phase = hasattr(self._scorer, "submit") and hasattr(self._scorer, "collect")
         block_base = sentence_base = 0
         from concurrent.futures import ThreadPoolExecutor
 
@@ -930,7 +960,10 @@ class OpenProvenceModel:
                 stage["assembly"] += t_asm
                 t0 = perf_counter()
                 if table_k.n_blocks:
-                    parts.append(self._scorer.run(table_k, threshold))
+                    if two_phase:  # data-parallel scorer: local device work now, ONE collective after the last chunk
+                        tickets.append(self._scorer.submit(table_k, threshold))
+                    else:
+                        parts.append(self._scorer.run(table_k, threshold))
                 stage["inference"] += perf_counter() - t0
                 for p in plans_k:  # chunk-local slots -> positions in the concatenated result arrays
                     p.block_slots = [b + block_base for b in p.block_slots]
@@ -938,6 +971,10 @@ class OpenProvenceModel:
                 block_base += table_k.n_blocks
                 sentence_base += table_k.n_sentences
                 plans.extend(plans_k)
+        if two_phase:
+            t0 = perf_counter()
+            parts = self._scorer.collect(tickets)
+            stage["inference"] += perf_counter() - t0
         preprocess_time = sum(timing.values())
         assembly_time, inference_time = stage["assembly"], stage["inference"]
         if parts:

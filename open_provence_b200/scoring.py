@@ -188,12 +188,9 @@ class DeviceScorer:
         return {"rank_score": rank_score, "frag_mean": frag_mean_h, "sent_prob": prob_h, "keep": keep_h, "near": near_h}
 
     @staticmethod
-    def _reevaluate_near(near_h, sent_index, sent_offsets, kept_logits, frag_mean_h, prob_h, keep_h, threshold) -> None:
-        """Sentences within the guard band of the threshold: recompute from the fp32 logits exactly as the
-        reference does on the CPU (standalone:2918-2920, 3081, 3118-3119); updates prob_h / keep_h in place."""
-        needed = set()
-        for s in np.nonzero(near_h)[0]:
-            needed.update(int(k) for k in sent_index[sent_offsets[s] : sent_offsets[s + 1]])
+    def exact_slot_means(needed: set, kept_logits) -> dict[int, float]:
+        """Fragment slots of ``needed`` whose logits are on THIS device -> mean keep-probability computed from the
+        fp32 logits exactly as the reference does on the CPU (standalone:2918-2920, 3081)."""
         slot_mean: dict[int, float] = {}
         for ranges, slots, prune in kept_logits:
             for j, slot in enumerate(slots):
@@ -201,18 +198,41 @@ class DeviceScorer:
                     a, b = int(ranges[j, 0]), int(ranges[j, 1])
                     logits = prune[a:b].cpu().numpy() if b > a else np.zeros((0, 2), np.float32)
                     slot_mean[int(slot)] = exact_fragment_mean(logits)
+        return slot_mean
+
+    @staticmethod
+    def _apply_exact_means(near_h, sent_index, sent_offsets, slot_mean, frag_mean_h, prob_h, keep_h, threshold) -> None:
+        """standalone:3118-3119 for the guard-band sentences, from exact fragment means; in place."""
         for s in np.nonzero(near_h)[0]:
             members = [int(k) for k in sent_index[sent_offsets[s] : sent_offsets[s + 1]]]
-            # fragments scored on another rank have no local logits: keep their device mean
             exact = exact_sentence_probability([slot_mean.get(k, float(frag_mean_h[k])) for k in members])
             prob_h[s] = exact
             keep_h[s] = exact > threshold
 
-    def score_blocks(self, table: BlockTable, blocks: np.ndarray):
+    def apply_exact(self, out: dict, table: BlockTable, slot_mean: dict[int, float], threshold: float) -> None:
+        """Sharded path: finish the guard-band sentences of ``out`` (a prune(reevaluate=False) result) from exact
+        fragment means gathered over all ranks."""
+        self._apply_exact_means(out["near"], np.asarray(table.sent_frag_index, dtype=np.int64),
+                                np.asarray(table.sent_offsets, dtype=np.int64), slot_mean, out["frag_mean"],
+                                out["sent_prob"], out["keep"], threshold)
+
+    @classmethod
+    def _reevaluate_near(cls, near_h, sent_index, sent_offsets, kept_logits, frag_mean_h, prob_h, keep_h, threshold) -> None:
+        """Sentences within the guard band of the threshold: recompute from the fp32 logits exactly as the
+        reference does on the CPU (standalone:2918-2920, 3081, 3118-3119); updates prob_h / keep_h in place."""
+        needed = set()
+        for s in np.nonzero(near_h)[0]:
+            needed.update(int(k) for k in sent_index[sent_offsets[s] : sent_offsets[s + 1]])
+        slot_mean = cls.exact_slot_means(needed, kept_logits)
+        cls._apply_exact_means(near_h, sent_index, sent_offsets, slot_mean, frag_mean_h, prob_h, keep_h, threshold)
+
+    def score_blocks(self, table: BlockTable, blocks: np.ndarray, host_scores: bool = True):
         """Forward + score conversion + fragment means for ``blocks`` (indices into the table).
 
-        Returns ``(rank_score np.float32 [n_blocks], frag_mean cuda fp32 [F], kept_logits)``; entries of
-        blocks that were not requested stay 0 (filled in by the all-gather in the sharded path)."""
+        Returns ``(rank_score [n_blocks], frag_mean cuda fp32 [F], kept_logits)``; entries of blocks that were
+        not requested stay 0 (filled in by the all-gather in the sharded path).  ``rank_score`` is a numpy fp32
+        array (one host sync) or, with ``host_scores=False``, a CUDA tensor (nothing synchronises: the sharded
+        path copies scores to the host once per process() call, after its all-gather)."""
         eng = self.engine
         dev = eng.device
         n_blocks = table.n_blocks
@@ -220,7 +240,7 @@ class DeviceScorer:
         frag_block = np.asarray(table.frag_block, dtype=np.int64)
         frag_local = np.asarray(table.frag_local, dtype=np.int64).reshape(-1, 2)
         n_frags = frag_block.shape[0]
-        rank_score = np.zeros(n_blocks, dtype=np.float32)
+        rank_score_dev = torch.zeros(max(n_blocks, 1), dtype=torch.float32, device=dev)
         frag_mean_dev = torch.zeros(max(n_frags, 1), dtype=torch.float32, device=dev)
         order = np.argsort(frag_block, kind="stable")  # fragment slots grouped by block
         first_slot = np.searchsorted(frag_block[order], np.arange(n_blocks + 1))
@@ -228,7 +248,6 @@ class DeviceScorer:
 
         blocks = np.asarray(blocks, dtype=np.int64)
         sub_lengths = [lengths[b] for b in blocks]
-        pending: list[tuple[np.ndarray, torch.Tensor]] = []
         for lo, hi in plan_launches(sub_lengths, self.max_tokens):
             chunk = blocks[lo:hi]
             cu = np.zeros(len(chunk) + 1, dtype=np.int32)
@@ -249,15 +268,16 @@ class DeviceScorer:
             means, score = eng.fragment_means(prune, d_ranges, rank)
             if slots.size:
                 frag_mean_dev[torch.from_numpy(slots).to(dev)] = means
-            pending.append((chunk, score))
+            rank_score_dev[torch.from_numpy(chunk).to(dev)] = score
             kept_logits.append((ranges, slots, prune))
-        for chunk, score in pending:  # one sync at the end instead of one per launch
-            rank_score[chunk] = score.cpu().numpy()
-        return rank_score, frag_mean_dev, kept_logits
+        if not host_scores:
+            return rank_score_dev[:n_blocks], frag_mean_dev, kept_logits
+        return rank_score_dev[:n_blocks].cpu().numpy(), frag_mean_dev, kept_logits  # one sync, after the last launch
 
     def prune(self, table: BlockTable, rank_score: np.ndarray, frag_mean_dev: torch.Tensor, kept_logits: list,
-              threshold: float) -> dict[str, np.ndarray]:
-        """Per-sentence mean / threshold on the device for every sentence of the call."""
+              threshold: float, reevaluate: bool = True) -> dict[str, np.ndarray]:
+        """Per-sentence mean / threshold on the device for every sentence of the call.  ``reevaluate=False`` leaves
+        the guard-band sentences (``near``) to the caller (sharded path: exact means come from the owning ranks)."""
         eng = self.engine
         dev = eng.device
         n_frags = len(table.frag_block)
@@ -275,6 +295,6 @@ class DeviceScorer:
             prob_h, keep_h, near_h = np.zeros(0), np.zeros(0, bool), np.zeros(0, bool)
         frag_mean_h = frag_mean_dev[:n_frags].cpu().numpy() if n_frags else np.zeros(0, np.float32)
 
-        if near_h.any():  # rare: re-evaluate with the reference's exact CPU arithmetic
+        if reevaluate and near_h.any():  # rare: re-evaluate with the reference's exact CPU arithmetic
             self._reevaluate_near(near_h, sent_index, sent_offsets, kept_logits, frag_mean_h, prob_h, keep_h, threshold)
         return {"rank_score": rank_score, "frag_mean": frag_mean_h, "sent_prob": prob_h, "keep": keep_h, "near": near_h}
