@@ -78,6 +78,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-pairs", type=int, default=32, help="pairs in the bounded CPU-baseline sample")
     ap.add_argument("--ref-pairs-per-step", type=int, default=4)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch blocks PER GPU; strong: --batch blocks IN TOTAL, dealt to the ranks by "
+                         "longest-processing-time-first on the FLOP cost model (sharding.lpt_assign)")
+    ap.add_argument("--launch-tokens", type=int, default=262144, help="packed tokens per forward launch (strong scaling)")
     ap.add_argument("--set-option", action="append", default=[], metavar="NAME=VALUE",
                     help="library tuning switch for A/B runs (opv_set_option), e.g. zigzag=0")
     return ap.parse_args()
@@ -275,34 +279,61 @@ def main() -> None:
     sd = syn.random_state_dict(cfg, seed=0)
     eng = Engine(cfg, sd, device=dev, dtype=args.dtype, num_labels=1)
     del sd
-    wl = syn.make_workload(cfg, args.batch, args.seq_len, mode=args.mode, seed=1234 + rank)
+    strong = args.scaling == "strong"
+    if strong:
+        # ONE global block list, identical on every rank; blocks dealt by LPT on the cost model, ragged or dense
+        from open_provence_b200.scoring import plan_launches
+        from open_provence_b200.sharding import block_cost, lpt_assign
+
+        wl_global = syn.make_workload(cfg, args.batch, args.seq_len, mode=args.mode, seed=1234)
+        costs = [block_cost(int(n), cfg["hidden_size"], cfg["intermediate_size"]) for n in wl_global["lengths"]]
+        shards = lpt_assign(costs, world)
+        mine = shards[rank]
+        wl = syn.slice_workload(wl_global, mine)
+        spans = plan_launches([int(n) for n in wl["lengths"]], args.launch_tokens)
+        parts = [syn.slice_workload(wl, np.arange(lo, hi)) for lo, hi in spans]
+        blocks_total = args.batch
+        shard_blocks = [int(len(sh)) for sh in shards]
+    else:
+        wl = syn.make_workload(cfg, args.batch, args.seq_len, mode=args.mode, seed=1234 + rank)
+        parts = [wl]
+        blocks_total = world * args.batch
+        shard_blocks = [args.batch] * world
     T = int(wl["ids"].shape[0])
     n_frags = int(wl["frag_ranges"].shape[0])
+    n_mine = int(wl["n_pairs"])
 
-    # host (pinned) and device-resident copies of the step inputs
-    host = {k: torch.from_numpy(wl[k]).pin_memory() for k in ("ids", "cu_seqlens", "frag_ranges", "sent_offsets", "sent_frag_index")}
-    d = {k: v.to(dev) for k, v in host.items()}
+    # host (pinned) and device-resident copies of the step inputs, one set per forward launch
+    KEYS = ("ids", "cu_seqlens", "frag_ranges", "sent_offsets", "sent_frag_index")
+    hosts = [{k: torch.from_numpy(np.ascontiguousarray(pt[k])).pin_memory() for k in KEYS} for pt in parts]
+    devs = [{k: v.to(dev) for k, v in h.items()} for h in hosts]
+    host, d = hosts[0], devs[0]
 
-    frag_max = n_frags
+    frag_max, blk_max = n_frags, n_mine
     if world > 1:
         import torch.distributed as dist
 
-        t = torch.tensor([n_frags], device=dev)
+        t = torch.tensor([n_frags, n_mine], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        frag_max = int(t.item())
-    rec_len = args.batch + 2 * frag_max
-    record = torch.zeros(rec_len, dtype=torch.float32, device=dev)
-    gathered = torch.empty(world * rec_len, dtype=torch.float32, device=dev) if world > 1 else None
+        frag_max, blk_max = int(t[0].item()), int(t[1].item())
+    rec_len = blk_max + 2 * frag_max
+    record = torch.zeros(max(rec_len, 1), dtype=torch.float32, device=dev)
+    gathered = torch.empty(world * record.numel(), dtype=torch.float32, device=dev) if world > 1 else None
 
     def step_device():
-        prune, rank_logits = eng.forward_packed(d["ids"], d["cu_seqlens"], wl["max_seqlen"])
-        frag_mean, score = eng.fragment_means(prune, d["frag_ranges"], rank_logits)
-        prob, keep, near = eng.sentence_prune(frag_mean, d["sent_offsets"], d["sent_frag_index"], THRESHOLD)
+        b_at = f_at = 0
+        for pt, dd in zip(parts, devs):
+            prune, rank_logits = eng.forward_packed(dd["ids"], dd["cu_seqlens"], pt["max_seqlen"])
+            frag_mean, score = eng.fragment_means(prune, dd["frag_ranges"], rank_logits)
+            prob, keep, near = eng.sentence_prune(frag_mean, dd["sent_offsets"], dd["sent_frag_index"], THRESHOLD)
+            if world > 1:
+                nb, nf = int(pt["n_pairs"]), int(pt["frag_ranges"].shape[0])
+                record[b_at : b_at + nb] = score
+                record[blk_max + f_at : blk_max + f_at + nf] = prob.float()
+                record[blk_max + frag_max + f_at : blk_max + frag_max + f_at + nf] = keep.float()
+                b_at, f_at = b_at + nb, f_at + nf
         if world > 1:
-            record[: args.batch] = score
-            record[args.batch : args.batch + n_frags] = prob.float()
-            record[args.batch + frag_max : args.batch + frag_max + n_frags] = keep.float()
-            dist.all_gather_into_tensor(gathered, record)
+            dist.all_gather_into_tensor(gathered, record)  # the one collective of the step
         return score, prob, keep
 
     def sync_all():
@@ -327,39 +358,49 @@ def main() -> None:
     elapsed_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     # forward launches (counted in the engine) + 3 prune-path kernels per step
-    launches = (eng.launch_count() - launches_before) // args.steps + 3
+    launches = (eng.launch_count() - launches_before) // args.steps + 3 * len(parts)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
-    value = world * args.batch / (ms_per_step * 1e-3)
+    value = blocks_total / (ms_per_step * 1e-3)
 
     # ---- e2e: the host-buffer call, H2D of the step's inputs and D2H of its results inside the timed region
-    h2d = sum(int(v.numel() * v.element_size()) for v in host.values())
+    h2d = sum(int(v.numel() * v.element_size()) for h in hosts for v in h.values())
+
+    def step_host():
+        outs = []
+        for pt, h in zip(parts, hosts):
+            outs.append(eng.score_packed_host(h["ids"], h["cu_seqlens"], pt["max_seqlen"], h["frag_ranges"],
+                                              h["sent_offsets"], h["sent_frag_index"], THRESHOLD))
+        if world > 1:
+            b_at = 0
+            for pt, o in zip(parts, outs):
+                record[b_at : b_at + int(pt["n_pairs"])] = o["rank_score"].to(dev, non_blocking=True)
+                b_at += int(pt["n_pairs"])
+            dist.all_gather_into_tensor(gathered, record)
+        return outs
+
     for _ in range(2):
-        out = eng.score_packed_host(host["ids"], host["cu_seqlens"], wl["max_seqlen"], host["frag_ranges"],
-                                    host["sent_offsets"], host["sent_frag_index"], THRESHOLD)
-    d2h = sum(int(v.numel() * v.element_size()) for v in out.values())
+        outs = step_host()
+    out = outs[0]
+    d2h = sum(int(v.numel() * v.element_size()) for o in outs for v in o.values())
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = eng.score_packed_host(host["ids"], host["cu_seqlens"], wl["max_seqlen"], host["frag_ranges"],
-                                    host["sent_offsets"], host["sent_frag_index"], THRESHOLD)
-        if world > 1:
-            record[: args.batch] = out["rank_score"].to(dev, non_blocking=True)
-            dist.all_gather_into_tensor(gathered, record)
+        step_host()
     sync_all()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * args.batch * args.steps / e2e_s
+    e2e_value = blocks_total * args.steps / e2e_s
 
     # ---- outputs of the benchmarked step itself (device-resident inputs, same kernels) for the in-run parity check
     gpu_check = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not strong:
         prune_l, rank_l = eng.forward_packed(d["ids"], d["cu_seqlens"], wl["max_seqlen"])
         frag_mean, score = eng.fragment_means(prune_l, d["frag_ranges"], rank_l)
         prob, keep, near = eng.sentence_prune(frag_mean, d["sent_offsets"], d["sent_frag_index"], THRESHOLD)
@@ -375,7 +416,8 @@ def main() -> None:
     eng.profile(True)
     prof_steps = min(3, args.steps)
     for _ in range(prof_steps):
-        eng.forward_packed(d["ids"], d["cu_seqlens"], wl["max_seqlen"])
+        for pt, dd in zip(parts, devs):
+            eng.forward_packed(dd["ids"], dd["cu_seqlens"], pt["max_seqlen"])
     prof = eng.profile_collect()
     eng.profile(False)
     profile_ms = {k: round(v["ms"] / prof_steps, 4) for k, v in prof.items()}
@@ -388,18 +430,19 @@ def main() -> None:
 
     peaks = measured_peaks()
     H, I, L = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_hidden_layers"]
+    Tl = T / max(1, len(parts))  # tokens per forward launch (average when a strong-scaling shard needs several)
     gemm_flops = {
-        "gemm_qkv_rope": 2.0 * T * 3 * H * H,
-        "gemm_wo_residual": 2.0 * T * H * H,
-        "gemm_wi_geglu": 2.0 * T * 2 * I * H,
-        "gemm_wo2_residual": 2.0 * T * H * I,
+        "gemm_qkv_rope": 2.0 * Tl * 3 * H * H,
+        "gemm_wo_residual": 2.0 * Tl * H * H,
+        "gemm_wi_geglu": 2.0 * Tl * 2 * I * H,
+        "gemm_wo2_residual": 2.0 * Tl * H * I,
     }
     dom = "gemm_wi_geglu"  # largest share of the algorithmic FLOPs (6HI of 8H^2+6HI per token per layer)
     dom_ms = prof[dom]["ms"] / max(1, prof[dom]["launches"])
     achieved_tf = gemm_flops[dom] / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
     flops_pair = syn.algorithmic_flops_per_pair(cfg, args.seq_len) if args.mode == "dense" else None
-    step_tf = (flops_pair * args.batch / (ms_per_step * 1e-3) / 1e12) if flops_pair else None
+    step_tf = (flops_pair * n_mine / (ms_per_step * 1e-3) / 1e12) if flops_pair else None  # rank 0's share of the step
     traffic = None
     traffic_file = ROOT / "profiles" / "roofline_traffic.json"
     if traffic_file.exists() and args.model == "base-130M" and args.seq_len == 2048 and args.batch == 64 and args.mode == "dense":
@@ -413,7 +456,7 @@ def main() -> None:
         "frac": round(achieved_tf / peak_tf, 4),
         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
         "traffic_source": traffic["source"] if traffic else None,
-        "algorithmic_bytes_per_launch": T * (2 * H + 2 * I) + 2 * 2 * I * H,
+        "algorithmic_bytes_per_launch": int(Tl * (2 * H + 2 * I) + 2 * 2 * I * H),
         "peak_kind": f"bf16 sustained, {peaks['source']} (MEASURED_PEAKS.json)",
         "flops_per_launch": gemm_flops[dom],
         "ms_per_launch": round(dom_ms, 4),
@@ -424,7 +467,7 @@ def main() -> None:
 
     cpu_baseline = None
     parity = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not strong:
         from oracle import hf_cpu_baseline as hb
 
         sd_cpu = syn.random_state_dict(cfg, seed=0)
@@ -449,14 +492,18 @@ def main() -> None:
         "warmup": max(3, args.warmup),
         "ms_per_step": round(ms_per_step, 4),
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": args.scaling,
         "vs_baseline": None,
         "dtype": args.dtype,
         "data": "synthetic",
         "config": {
-            "workload": f"{args.model} seq_len={args.seq_len} batch={args.batch} blocks per GPU, {args.mode}, pre-tokenised, random-init weights",
+            "workload": (f"{args.model} seq_len={args.seq_len} batch={args.batch} blocks "
+                         f"{'in total (LPT-sharded over the ranks)' if strong else 'per GPU'}, {args.mode}, pre-tokenised, "
+                         "random-init weights"),
             "tokens_per_step_per_gpu": T,
             "sentences_per_step_per_gpu": n_frags,
+            "blocks_per_rank": shard_blocks,
+            "forward_launches_per_step_per_gpu": len(parts),
             "threshold": THRESHOLD,
             "parallelism": f"dp{world} (blocks sharded, weights replicated, one all-gather of scores per step)" if world > 1 else "single GPU",
             "l2": "per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush",

@@ -150,3 +150,36 @@ def algorithmic_flops_per_pair(cfg: dict[str, Any], S: int, num_labels: int = 1)
     band = int((np.minimum(S - 1, i + half) - np.maximum(0, i - half) + 1).sum())
     return float(S * L * (8 * H * H + 6 * H * I) + n_glob * 4 * H * S * S + (L - n_glob) * 4 * H * band
                  + 2 * H * H + 2 * H * num_labels + S * 4 * H)
+
+
+def slice_workload(wl: dict[str, Any], blocks) -> dict[str, Any]:
+    """The sub-workload made of ``blocks`` (indices into ``wl``, kept in the given order), re-packed: same keys as
+    :func:`make_workload`.  Used to shard a fixed global block list over ranks / launches (strong scaling)."""
+    blocks = np.asarray(blocks, dtype=np.int64)
+    cu = wl["cu_seqlens"].astype(np.int64)
+    lengths = wl["lengths"][blocks]
+    new_cu = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    ids = np.concatenate([wl["ids"][cu[b] : cu[b + 1]] for b in blocks]) if blocks.size else np.zeros(0, np.int32)
+    ranges, frag_block = [], []
+    order = np.argsort(wl["frag_block"], kind="stable")
+    first = np.searchsorted(wl["frag_block"][order], np.arange(len(cu)))
+    for k, b in enumerate(blocks):
+        sel = order[first[b] : first[b + 1]]
+        ranges.append(wl["frag_ranges"][sel].astype(np.int64) - cu[b] + new_cu[k])
+        frag_block.append(np.full(sel.size, k, dtype=np.int32))
+    ranges = np.concatenate(ranges) if ranges else np.zeros((0, 2), np.int64)
+    n_frags = int(ranges.shape[0])
+    return {
+        "ids": ids.astype(np.int32),
+        "cu_seqlens": new_cu.astype(np.int32),
+        "lengths": lengths.astype(np.int32),
+        "max_seqlen": int(lengths.max()) if blocks.size else 0,
+        "frag_ranges": ranges.astype(np.int32).reshape(n_frags, 2),
+        "sent_offsets": np.arange(n_frags + 1, dtype=np.int32),
+        "sent_frag_index": np.arange(n_frags, dtype=np.int32),
+        "frag_block": np.concatenate(frag_block).astype(np.int32) if frag_block else np.zeros(0, np.int32),
+        "n_pairs": int(blocks.size),
+        "seq_len": wl["seq_len"],
+        "mode": wl["mode"],
+        "global_blocks": blocks.astype(np.int64),
+    }
