@@ -39,6 +39,11 @@ def metric_name(args) -> str:
 
 
 UNIT = "pairs/s"
+# /root/reference cannot travel to the GPU box, so the timed CPU arm is the port (oracle/hf_cpu_baseline.py: the reference's
+# library forward + its numpy / torch post-processing).  Checked once in the build container against the UNMODIFIED
+# reference's own loop (process() -> _run_inference_batches, standalone:2761-2939) on the same blocks and weights:
+PORT_NOTE = ("port loop = 0.99 x the time of the unmodified reference's process() on the same 4 x 2048-token blocks, identical "
+             "scores (profiles/r2_reference_loop_vs_port.md, tools/reference_loop_compare.py)")
 THRESHOLD = 0.1
 
 
@@ -208,7 +213,7 @@ def run_reference(args, world: int, rank: int) -> None:
         "config": {"workload": f"{args.model} seq_len={args.seq_len} {args.mode}, {per_step} blocks per step (bounded CPU sample)",
                    "transformers": __import__("transformers").__version__},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
-                         "host_cpus": os.cpu_count()},
+                         "host_cpus": os.cpu_count(), "port_vs_reference_loop": PORT_NOTE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -481,6 +486,7 @@ def main() -> None:
             "kind": "port",
             "sample": f"first {args.cpu_pairs} blocks of the same workload ({res['seconds']:.1f} s), HF ModernBERT fp32 sdpa on CPU + numpy prune",
             "host_cpus": os.cpu_count(),
+            "port_vs_reference_loop": PORT_NOTE,
         }
 
     line = {
