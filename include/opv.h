@@ -123,9 +123,9 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
  * at opv_create(), the single-op entry points (opv_op_*) read them at call time; opv_engine_set_option() changes one
  * engine only (everything except "gemm_pair", which is fixed at creation).  Both are thread-safe.
  * "attention_impl": bf16 attention kernel, 1 = default (one softmax thread per query row, two CTAs per SM, for global
- * layers; two threads per row for sliding-window layers), 2 = one thread per row with P staged through shared memory,
+ * layers; the one-pass kernel for sliding-window layers with window <= 128, two threads per row for wider windows), 2 = one thread per row with P staged through shared memory,
  * 3 = two threads per row everywhere, 4 = one thread per row everywhere, 5 = two-Q-tile kernel (one CTA per SM, 16
- * softmax warps, K / V shared by two query tiles) everywhere.  "attention_trace_ptr": device buffer for the clock64() timeline of
+ * softmax warps, K / V shared by two query tiles) everywhere, 6 = one-pass sliding-window kernel (window <= 128).  "attention_trace_ptr": device buffer for the clock64() timeline of
  * tools/attn_check.py (0 = off, the product setting).  "gemm_pair": 1 = CTA-pair (cta_group::2) GEMM for 256-wide
  * tiles (default), 0 = single-CTA kernel.  "gemm_group_rows": row-grouped tile order of the RoPE GEMM (default 1).
  * "pdl": 1 = GEMM / attention / LayerNorm kernels are launched with programmatic stream serialization so that each

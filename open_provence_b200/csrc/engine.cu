@@ -15,6 +15,7 @@
 #include "../../include/opv.h"
 #include "attention_simt.cuh"
 #include "attention_tcgen05.cuh"
+#include "attention_tcgen05_local.cuh"
 #include "attention_tcgen05_pp.cuh"
 #include "attention_tcgen05_v3.cuh"
 #include "common.cuh"
@@ -100,9 +101,10 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 // defaults at call time.  Nothing below reads a process-global while launching: each extern "C" entry point copies
 // the options of ITS engine (or the defaults) and the SM count of the CURRENT device into thread-local state.
 struct Options {
-  // bf16 attention kernel: 1 = default (one-thread-per-row kernel for global layers, two-threads-per-row kernel for
-  // sliding-window layers), 2 = one-thread-per-row with P in smem, 3 = two-threads-per-row everywhere,
-  // 4 = one-thread-per-row (P in TMEM, 2 CTAs / SM) everywhere, 5 = two-Q-tile kernel (1 CTA / SM) everywhere
+  // bf16 attention kernel: 1 = default (one-thread-per-row kernel for global layers; one-pass kernel for sliding-window
+  // layers with window <= 128, two-threads-per-row kernel for wider windows), 2 = one-thread-per-row with P in smem, 3 = two-threads-per-row everywhere,
+  // 4 = one-thread-per-row (P in TMEM, 2 CTAs / SM) everywhere, 5 = two-Q-tile kernel (1 CTA / SM) everywhere,
+  // 6 = one-pass sliding-window kernel (window <= 128; what 1 uses for such layers)
   int attention_impl = 1;
   int attention_debug = 0;               // timing experiments of the two-Q-tile kernel (attention_tcgen05_pp.cuh), 0 = off
   long long* attention_trace = nullptr;  // device buffer for clock64() stamps (tools/attn_check.py); nullptr in the product
@@ -203,6 +205,8 @@ int ensure_device_setup() {
                                   opv::FaSmemLayout<false>::kTotal));
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   opv::Fa3SmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_local_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::LoSmemLayout::kTotal));
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_pp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   opv::PpSmemLayout::kTotal));
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_pp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -408,8 +412,18 @@ int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, i
     const int64_t total_tiles = static_cast<int64_t>(n_seqs) * heads * tiles_per_seq;
     if (total_tiles > 0x7fffffffLL) return fail(OPV_ERR_UNSUPPORTED, "too many attention tiles for one launch");
     const int grid = static_cast<int>(total_tiles < 2 * g_num_sms ? total_tiles : 2 * g_num_sms);
-    // sliding-window layers: two softmax threads per row (0.156 vs 0.176 ms per layer at 64 x 2048); 3 / 4 force one
-    // of the 2-CTAs-per-SM kernels everywhere
+    // sliding-window layers whose band fits one 256-key score tile (window <= 128, every published checkpoint): the
+    // one-pass kernel; 6 forces it (and fails for wider windows), 3 / 4 force one of the online-softmax kernels
+    if (impl == 6 && (half_window < 0 || half_window > opv::kLoMaxHalfWindow))
+      return fail(OPV_ERR_UNSUPPORTED, "attention_impl 6 (one-pass sliding window) needs 0 <= half_window <= %d",
+                  opv::kLoMaxHalfWindow);
+    if (impl == 6 || (impl == 1 && half_window >= 0 && half_window <= opv::kLoMaxHalfWindow)) {
+      launch_pdl(opv::attention_local_onepass_kernel, dim3(grid), dim3(opv::kLoThreads), opv::LoSmemLayout::kTotal, s,
+                 *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq, pdl_late_flag());
+      OPV_LAUNCH_CHECK("attention_local_onepass_kernel");
+      return OPV_OK;
+    }
+    // wider windows: two softmax threads per row (0.156 vs 0.176 ms per layer at 64 x 2048)
     if (impl == 3 || (impl == 1 && half_window >= 0))
       launch_pdl(opv::attention_tcgen05_v3_kernel, dim3(grid), dim3(opv::kFa3Threads), opv::Fa3SmemLayout::kTotal, s,
                  *tm_qkv, static_cast<__nv_bfloat16*>(out), cu, H, half_window, n_seqs, tiles_per_seq,
@@ -436,7 +450,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int set_option_in(Options& o, const char* name, int64_t value) {
   if (strcmp(name, "attention_impl") == 0) {
-    if (value < 1 || value > 5) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_impl must be 1 .. 5");
+    if (value < 1 || value > 6) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_impl must be 1 .. 6");
     o.attention_impl = static_cast<int>(value);
   } else if (strcmp(name, "attention_debug") == 0) {
     if (value < 0 || value > 4) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_debug must be 0 .. 4");

@@ -220,6 +220,30 @@ def test_attention_bf16_impls(impl, half_window):
     assert err < tol, f"attention impl={impl} window={half_window}: max err {err:.3e} (tol {tol:.3e})"
 
 
+@pytest.mark.parametrize("half_window", [64, 8, 1, 0, 33])
+def test_attention_local_onepass(half_window):
+    """One-pass sliding-window kernel (window <= 128): the whole band of a 128-query tile in one 256-key score tile."""
+    heads = 3
+    lengths = ATT_LENGTHS + [1100, 2048]
+    total = sum(lengths)
+    g = torch.Generator().manual_seed(21)
+    qkv = (torch.randn((total, 3 * heads * 64), generator=g) * 1.5).to(torch.bfloat16).to(DEV)
+    cu = torch.tensor([0] + list(np.cumsum(lengths)), dtype=torch.int32, device=DEV)
+    ops.set_option("attention_impl", 6)
+    try:
+        out = ops.attention(qkv, cu, max(lengths), heads, half_window)
+        torch.cuda.synchronize()
+        with pytest.raises(NotImplementedError, match="half_window <= 64"):
+            ops.attention(qkv, cu, max(lengths), heads, 65)
+    finally:
+        ops.set_option("attention_impl", 1)
+    ref = _attention_ref(qkv, lengths, heads, half_window)
+    err = (out.double() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all()
+    tol = 6e-3 * max(1.0, ref.abs().max().item())
+    assert err < tol, f"one-pass local attention window={half_window}: max err {err:.3e} (tol {tol:.3e})"
+
+
 def test_rope_and_geglu_unfused():
     hidden, m, inter = 128, 500, 256
     cos, sin = rope_table(1024, 64, 10000.0)
