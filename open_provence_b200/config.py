@@ -91,7 +91,10 @@ class OpenProvenceConfig:
         return cfg
 
     def to_dict(self) -> dict[str, Any]:
-        out = {
+        """Known keys + every unknown key the loaded ``config.json`` carried (``self.extra``: vocab_size, hidden_size,
+        transformers_version, ... -- the reference's config round-trips them, encoder.py:1050-1088)."""
+        out = dict(self.extra)
+        out.update({
             "model_type": self.model_type,
             "mode": self.mode,
             "base_model_name_or_path": self.base_model_name_or_path,
@@ -103,7 +106,7 @@ class OpenProvenceConfig:
             "num_pruning_labels": self.num_pruning_labels,
             "encoder_architecture": self.encoder_architecture,
             "default_threadshold": self.default_threadshold,
-        }
+        })
         return out
 
     def resolve_default_threshold(self) -> float:

@@ -198,9 +198,26 @@ class OpenProvenceEncoder:
         cfg = self.config.to_dict()
         cfg["max_length"] = int(self.max_length)
         cfg["mode"] = "reranking_pruning"
-        from .hf_auto import with_auto_map
+        from .hf_auto import ARCHITECTURES, AUTO_MAP, with_auto_map
 
-        cfg = with_auto_map(cfg)  # encoder.py:1078-1085: the reference's Auto* entry points
+        # encoder.py:1078-1094: the reference writes ``auto_map`` AND copies modeling_open_provence_standalone.py next to
+        # the weights, so that stock ``AutoModel.from_pretrained(dir, trust_remote_code=True)`` finds the class.  That
+        # file belongs to the reference; it is carried over from the checkpoint this encoder was loaded from when it is
+        # there, and ``auto_map`` is only written when the module it names is actually in the directory.
+        shipped = False
+        source = Path(getattr(self.config, "_name_or_path", "") or "")
+        modules = {entry.split(".")[0] for entry in AUTO_MAP.values()}
+        for module in modules:
+            src = source / f"{module}.py"
+            if source.is_dir() and src.is_file():
+                if src.resolve() != (out / src.name).resolve():
+                    (out / src.name).write_bytes(src.read_bytes())
+                shipped = True
+        shipped = shipped and all((out / f"{module}.py").is_file() for module in modules)
+        cfg.pop("auto_map", None)
+        cfg["architectures"] = list(ARCHITECTURES)
+        if shipped:
+            cfg = with_auto_map(cfg)
         (out / "config.json").write_text(json.dumps(cfg, indent=2, ensure_ascii=False, default=str))
         if self.tokenizer is not None:
             self.tokenizer.save_pretrained(str(out))

@@ -407,8 +407,9 @@ class OpenProvenceModel:
         return_dict: bool | None = None,
         **kwargs: Any,
     ) -> OpenProvenceOutput | tuple[torch.Tensor, ...]:
-        """Same contract as standalone:1666-1739: ``[B, S]`` right-padded ids (+ mask) ->
-        ``ranking_logits [B, num_labels]`` and ``pruning_logits [B, S, 2]`` (fp32; zeros at padding)."""
+        """Same contract as standalone:1666-1739: ``[B, S]`` ids (+ mask) -> ``ranking_logits [B, num_labels]`` and
+        ``pruning_logits [B, S, 2]`` (fp32; zeros at masked columns, where the reference returns the backbone's output
+        for the [PAD] token -- no caller reads those: ``context_ranges`` never cover padding)."""
         if input_ids is None:
             raise ValueError("input_ids must be provided")
         if self.engine is None:
@@ -423,10 +424,11 @@ class OpenProvenceModel:
             mask = torch.ones((B, S), dtype=torch.bool, device=dev)
         else:
             mask = attention_mask.to(dev).bool()
+        # Any mask is accepted: the kept tokens of a row are compacted into one packed sequence and the logits are
+        # scattered back to their columns (masked columns: logit 0).  Positions (RoPE, sliding window, CLS = first kept
+        # token) count KEPT tokens, exactly as in the reference's unpadded flash-attention path; for right-padded
+        # batches -- what every caller in the reference produces -- that is also what its eager / sdpa path computes.
         lengths = mask.sum(dim=1)
-        prefix = torch.arange(S, device=dev)[None, :] < lengths[:, None]
-        if not torch.equal(prefix, mask):
-            raise ValueError("attention_mask must be right-padded (a prefix of ones per row)")
         if bool((lengths == 0).any()):
             raise ValueError("every row of attention_mask must keep at least one token")
         cu = torch.zeros(B + 1, dtype=torch.int32, device=dev)

@@ -99,10 +99,21 @@ def test_forward_padded_interface(model_fp32, forward_golden):
     assert isinstance(tup, tuple) and len(tup) == 2
     with pytest.raises(ValueError, match="input_ids must be provided"):
         model_fp32.forward(input_ids=None)
-    bad = mask.clone()
-    bad[-1, 0] = 0
-    with pytest.raises(ValueError, match="right-padded"):
-        model_fp32.forward(input_ids=ids, attention_mask=bad)
+    # left padding (and any other mask): kept tokens are compacted, logits scattered back to their columns
+    n = int(mask[1].sum())
+    shifted_ids, shifted_mask = ids.clone(), mask.clone()
+    pad = ids.shape[1] - n
+    if pad > 0:
+        shifted_ids[1] = torch.cat([ids[1, n:], ids[1, :n]])
+        shifted_mask[1] = torch.cat([mask[1, n:], mask[1, :n]])
+        left = model_fp32.forward(input_ids=shifted_ids, attention_mask=shifted_mask, return_dict=True)
+        assert torch.equal(left.ranking_logits, out.ranking_logits)
+        assert torch.equal(left.pruning_logits[1, pad:], out.pruning_logits[1, :n])
+        assert torch.count_nonzero(left.pruning_logits[1, :pad]) == 0
+    empty = mask.clone()
+    empty[-1] = 0
+    with pytest.raises(ValueError, match="at least one token"):
+        model_fp32.forward(input_ids=ids, attention_mask=empty)
 
 
 def test_prune_kernels_match_oracle(model_fp32):

@@ -72,11 +72,21 @@ def test_auto_model_loads_the_engine_and_token_wrapper_exposes_pruning_logits(ti
     assert abs(float(out.loss) - float(want)) < 1e-6
     assert tok(input_ids=ids, attention_mask=mask, return_dict=False)[0].shape == b.logits.shape
 
-    # a checkpoint written by this package carries the reference's auto_map and loads back through AutoModel
+    # a checkpoint written by this package loads back through AutoModel.  ``auto_map`` is only written when the remote
+    # code module it names travels with the checkpoint (stock transformers fails on a dangling auto_map)
     enc = OpenProvenceEncoder.from_pretrained(tiny_ckpt_dir, device="cuda", dtype="fp32")
     enc.save_pretrained(tmp_path / "ckpt")
     saved = json.loads((tmp_path / "ckpt" / "config.json").read_text())
-    assert saved["auto_map"] == hf_auto.AUTO_MAP and saved["architectures"] == hf_auto.ARCHITECTURES
+    assert "auto_map" not in saved and saved["architectures"] == hf_auto.ARCHITECTURES
+    assert saved["transformers_version"] and saved["id2label"]  # unknown config keys round-trip (config.extra)
+    import shutil
+
+    src = tmp_path / "src_with_remote_code"
+    shutil.copytree(tiny_ckpt_dir, src)
+    (src / "modeling_open_provence_standalone.py").write_text("# the reference's remote-code module travels with the checkpoint\n")
+    OpenProvenceEncoder.from_pretrained(src, device="cuda", dtype="fp32").save_pretrained(tmp_path / "ckpt2")
+    saved2 = json.loads((tmp_path / "ckpt2" / "config.json").read_text())
+    assert saved2["auto_map"] == hf_auto.AUTO_MAP and (tmp_path / "ckpt2" / "modeling_open_provence_standalone.py").is_file()
     again = AutoModel.from_pretrained(str(tmp_path / "ckpt"), device="cuda", dtype="float32")
     c = again(input_ids=ids, attention_mask=mask, return_dict=True)
     assert torch.equal(c.ranking_logits, a.ranking_logits)
