@@ -56,7 +56,7 @@ def random_state_dict(cfg: dict[str, Any], seed: int = 0, num_labels: int = 1) -
     """fp32 CPU state dict with the reference's key names.
 
     Stds follow HF:379-384 (in = 0.02, out = 0.02/sqrt(2L), final_out = H^-0.5).  The pruning head is
-    N(0, 0.5^2) with bias (0, logit(0.1)) so per-sentence means straddle the 0.1 threshold (section 8d).
+    N(0, 1.06^2 / H) with bias (0, logit(0.05)) so per-sentence means straddle the 0.1 threshold (section 8d).
     LayerNorm gains get a small jitter so a dropped gain cannot go unnoticed.
     """
     gen = torch.Generator().manual_seed(seed)
@@ -86,8 +86,11 @@ def random_state_dict(cfg: dict[str, Any], seed: int = 0, num_labels: int = 1) -
     sd[p + "head.norm.weight"] = gain(H)
     sd[p + "classifier.weight"] = _trunc_normal((num_labels, H), H**-0.5, cutoff, gen)
     sd[p + "classifier.bias"] = torch.zeros(num_labels)
-    sd["pruning_head.classifier.weight"] = torch.randn(2, H, generator=gen) * 0.5
-    sd["pruning_head.classifier.bias"] = torch.tensor([0.0, math.log(0.1 / 0.9)])
+    # keep-logit margin ~ N(log(0.05 / 0.95), 1.5^2) per token: token keep-probabilities spread over (0, 0.5) and the
+    # per-sentence means land on BOTH sides of the default 0.1 threshold (r1 used N(0, 0.5^2) weights: |logit| ~ 40,
+    # saturated probabilities, 99.9 % of the sentences kept -- a weak check of the keep decisions)
+    sd["pruning_head.classifier.weight"] = torch.randn(2, H, generator=gen) * (1.06 / math.sqrt(H))
+    sd["pruning_head.classifier.bias"] = torch.tensor([0.0, math.log(0.05 / 0.95)])
     return sd
 
 
