@@ -45,7 +45,13 @@ typedef enum opv_status {
  * softmax and GELU are always fp32). */
 typedef enum opv_dtype {
   OPV_DTYPE_BF16 = 0, /* tcgen05 kind::f16 tensor-core path (the product path) */
-  OPV_DTYPE_F32 = 1   /* FFMA parity mode (1e-5 against the fp32 reference forward) */
+  OPV_DTYPE_F32 = 1,  /* FFMA parity mode (1e-5 against the fp32 reference forward) */
+  /* fp32 parity THROUGH THE TENSOR-CORE PIPELINE: activations fp32 as in OPV_DTYPE_F32, but every projection runs on
+   * the product's tcgen05 / TMA / TMEM GEMM kernel as six bf16 passes over 3-way splits of both operands
+   * (x = hi + mid + lo, 3 x 8 mantissa bits; hi.hi + hi.mid + mid.hi + mid.mid + hi.lo + lo.hi accumulated in fp32 by
+   * the RESIDUAL epilogue's TMA reduce-add).  Weights: d_wqkv / d_wo / d_wi / d_wo2 point to bf16 [3][out][in]
+   * (hi | mid | lo planes); everything else as in OPV_DTYPE_F32. */
+  OPV_DTYPE_F32_TC = 2
 } opv_dtype;
 
 /* What HF's ModernBertConfig carries for the backbone (configuration_modernbert.py:77-167) plus

@@ -14,6 +14,7 @@ OPV_ABI_VERSION = 2
 OPV_MAX_LAYERS = 64
 OPV_DTYPE_BF16 = 0
 OPV_DTYPE_F32 = 1
+OPV_DTYPE_F32_TC = 2
 EPI_STORE, EPI_ROPE, EPI_RESIDUAL, EPI_GEGLU = 0, 1, 2, 3
 
 PROF_CLASSES = (

@@ -490,7 +490,7 @@ struct opv_engine {
   opv_config cfg;
   opv_weights w;
   std::vector<opv_layer_weights> layers;
-  std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_wi, tm_wo2;  // bf16 mode only
+  std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_wi, tm_wo2;  // bf16 mode: one per layer; F32_TC: three (hi | mid | lo) per layer
   bool gemm_pair = true;                                   // CTA-pair GEMM kernel for the 256-wide tiles
   Options opt;                                             // snapshot of the defaults at opv_create (+ opv_engine_set_option)
   int device;
@@ -531,12 +531,12 @@ struct LaunchScope {
 };
 
 struct WorkspaceLayout {
-  size_t h, x, qkv, attn, act, u, pos, cls, y, pool, total;
+  size_t h, x, qkv, attn, act, u, pos, cls, y, pool, split, total;
 };
 
 static WorkspaceLayout workspace_layout(const opv_engine* e, int64_t T, int64_t n_seqs) {
   const size_t H = e->cfg.hidden_size, I = e->cfg.intermediate_size, elt = e->elt;
-  const bool unfused = e->cfg.dtype == OPV_DTYPE_F32 || !e->cfg.fuse_epilogues;
+  const bool unfused = e->cfg.dtype != OPV_DTYPE_BF16 || !e->cfg.fuse_epilogues;
   WorkspaceLayout l;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -557,6 +557,8 @@ static WorkspaceLayout workspace_layout(const opv_engine* e, int64_t T, int64_t 
   l.y = take(seqs * H * 4);    // rank head: gelu(dense(cls))
   // mean pooling: per-chunk sums of the final-normed rows (slot = begin / chunk + s + c, pointwise.cuh)
   l.pool = take(e->cfg.classifier_pooling ? (rows / opv::kPoolChunkRows + seqs + 2) * H * 4 : 0);
+  // F32_TC: hi | mid | lo bf16 planes of the current GEMM's A operand (widest: the [T, I] GeGLU output)
+  l.split = take(e->cfg.dtype == OPV_DTYPE_F32_TC ? 3 * rows * (I > H ? I : H) * 2 : 0);
   l.total = off;
   return l;
 }
@@ -587,7 +589,7 @@ int opv_create(const opv_config* cfg, const opv_weights* w, int device, opv_hand
   if (cfg->classifier_pooling != 0 && cfg->classifier_pooling != 1)
     return fail(OPV_ERR_INVALID_ARGUMENT, "classifier_pooling must be 0 (cls) or 1 (mean), got %d",
                 cfg->classifier_pooling);
-  if (cfg->dtype != OPV_DTYPE_BF16 && cfg->dtype != OPV_DTYPE_F32)
+  if (cfg->dtype != OPV_DTYPE_BF16 && cfg->dtype != OPV_DTYPE_F32 && cfg->dtype != OPV_DTYPE_F32_TC)
     return fail(OPV_ERR_INVALID_ARGUMENT, "unknown dtype %d", cfg->dtype);
   if (!w->h_layers) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_create: weights.h_layers is null");
   DeviceGuard guard;
@@ -598,7 +600,7 @@ int opv_create(const opv_config* cfg, const opv_weights* w, int device, opv_hand
   e->cfg = *cfg;
   e->w = *w;
   e->device = device;
-  e->elt = cfg->dtype == OPV_DTYPE_BF16 ? 2 : 4;
+  e->elt = cfg->dtype == OPV_DTYPE_BF16 ? 2 : 4;  // activations; F32_TC keeps fp32 activations
   e->opt = defaults_snapshot();
   e->gemm_pair = e->opt.gemm_pair != 0;
   e->layers.assign(w->h_layers, w->h_layers + cfg->num_layers);
@@ -635,6 +637,34 @@ int opv_create(const opv_config* cfg, const opv_weights* w, int device, opv_hand
       if (rc) {
         delete e;
         return rc;
+      }
+    }
+  }
+  if (cfg->dtype == OPV_DTYPE_F32_TC) {
+    const int bn_qkv = gemm_block_n(3 * H, opv::kEpiResidual), bn_h = gemm_block_n(H, opv::kEpiResidual);
+    const int bn_wi = gemm_block_n(2 * I, opv::kEpiResidual);
+    if (!bn_qkv || !bn_h || !bn_wi) {
+      delete e;
+      return fail(OPV_ERR_UNSUPPORTED, "projection widths (3H=%d, H=%d, 2I=%d) do not tile", 3 * H, H, 2 * I);
+    }
+    const bool pair = e->gemm_pair;
+    e->tm_wqkv.resize(3 * cfg->num_layers);
+    e->tm_wo.resize(3 * cfg->num_layers);
+    e->tm_wi.resize(3 * cfg->num_layers);
+    e->tm_wo2.resize(3 * cfg->num_layers);
+    for (int l = 0; l < cfg->num_layers; ++l) {
+      const opv_layer_weights& lw = e->layers[l];
+      for (int p = 0; p < 3; ++p) {  // hi | mid | lo planes, [out][in] bf16 each
+        using bf16 = __nv_bfloat16;
+        int rc = 0;
+        rc = rc ? rc : make_tmap_bf16(&e->tm_wqkv[3 * l + p], static_cast<const bf16*>(lw.d_wqkv) + (size_t)p * 3 * H * H, 3 * H, H, weight_box_rows(bn_qkv, pair));
+        rc = rc ? rc : make_tmap_bf16(&e->tm_wo[3 * l + p], static_cast<const bf16*>(lw.d_wo) + (size_t)p * H * H, H, H, weight_box_rows(bn_h, pair));
+        rc = rc ? rc : make_tmap_bf16(&e->tm_wi[3 * l + p], static_cast<const bf16*>(lw.d_wi) + (size_t)p * 2 * I * H, 2 * I, H, weight_box_rows(bn_wi, pair));
+        rc = rc ? rc : make_tmap_bf16(&e->tm_wo2[3 * l + p], static_cast<const bf16*>(lw.d_wo2) + (size_t)p * H * I, H, I, weight_box_rows(bn_h, pair));
+        if (rc) {
+          delete e;
+          return rc;
+        }
       }
     }
   }
@@ -791,6 +821,29 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       if (rc) return rc;
     }
   } else {
+    // fp32 activations.  OPV_DTYPE_F32: FFMA GEMMs.  OPV_DTYPE_F32_TC: the SAME launch sequence, but every projection is
+    // six passes of the product's tcgen05 GEMM (RESIDUAL epilogue = fp32 TMA reduce-add) over 3-way bf16 splits.
+    const bool tc = c.dtype == OPV_DTYPE_F32_TC;
+    __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>(ws + wl.split);
+    auto gemm32 = [&](bool accumulate, const float* a, const float* w_f32, const CUtensorMap* w_planes, float* out_c,
+                      int N, int K) -> int {
+      if (!tc) return gemm_f32(accumulate, a, w_f32, out_c, T, N, K, N, stream);
+      const int64_t n_elems = T * K;
+      opv::split3_bf16_kernel<<<g_num_sms * 8, 256, 0, stream>>>(a, planes, n_elems);
+      OPV_LAUNCH_CHECK("split3_bf16_kernel");
+      if (!accumulate) OPV_CUDA(cudaMemsetAsync(out_c, 0, static_cast<size_t>(T) * N * sizeof(float), stream));
+      CUtensorMap tm_a[3], tm_c;
+      for (int p = 0; p < 3; ++p)
+        if (int r = make_tmap_bf16(&tm_a[p], planes + p * n_elems, T, K, opv::kGemmBlockM)) return r;
+      if (int r = make_tmap_2d(&tm_c, out_c, true, T, N, opv::kGemmBlockM)) return r;
+      opv::GemmEpilogueArgs er{};
+      // smallest terms first: mid.mid, hi.lo, lo.hi, hi.mid, mid.hi, hi.hi  (a plane, w plane)
+      static const int order[6][2] = {{1, 1}, {0, 2}, {2, 0}, {0, 1}, {1, 0}, {0, 0}};
+      for (const auto& pq : order)
+        if (int r = gemm_bf16(opv::kEpiResidual, e->gemm_pair, tm_a[pq[0]], w_planes[pq[1]], tm_c, er, T, N, K, stream)) return r;
+      e->launches += 6;  // + the split (the scope counts one)
+      return OPV_OK;
+    };
     float* xf = static_cast<float*>(x);
     float* qf = static_cast<float*>(qkv);
     float* af = static_cast<float*>(attn);
@@ -812,7 +865,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       if (rc) return rc;
       {
         LaunchScope sc(e, stream, OPV_PROF_GEMM_QKV);
-        rc = gemm_f32(false, xf, static_cast<const float*>(lw.d_wqkv), qf, T, 3 * H, H, 3 * H, stream);
+        rc = gemm32(false, xf, static_cast<const float*>(lw.d_wqkv), tc ? &e->tm_wqkv[3 * l] : nullptr, qf, 3 * H, H);
       }
       if (rc) return rc;
       {
@@ -830,7 +883,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       if (rc) return rc;
       {
         LaunchScope sc(e, stream, OPV_PROF_GEMM_WO);
-        rc = gemm_f32(true, af, static_cast<const float*>(lw.d_wo), h, T, H, H, H, stream);
+        rc = gemm32(true, af, static_cast<const float*>(lw.d_wo), tc ? &e->tm_wo[3 * l] : nullptr, h, H, H);
       }
       if (rc) return rc;
       {
@@ -840,7 +893,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       if (rc) return rc;
       {
         LaunchScope sc(e, stream, OPV_PROF_GEMM_WI);
-        rc = gemm_f32(false, xf, static_cast<const float*>(lw.d_wi), uf, T, 2 * I, H, 2 * I, stream);
+        rc = gemm32(false, xf, static_cast<const float*>(lw.d_wi), tc ? &e->tm_wi[3 * l] : nullptr, uf, 2 * I, H);
       }
       if (rc) return rc;
       {
@@ -850,7 +903,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       }
       {
         LaunchScope sc(e, stream, OPV_PROF_GEMM_WO2);
-        rc = gemm_f32(true, actf, static_cast<const float*>(lw.d_wo2), h, T, H, I, H, stream);
+        rc = gemm32(true, actf, static_cast<const float*>(lw.d_wo2), tc ? &e->tm_wo2[3 * l] : nullptr, h, H, I);
       }
       if (rc) return rc;
     }

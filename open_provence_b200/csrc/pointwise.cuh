@@ -405,4 +405,20 @@ __global__ void sentence_prune_kernel(const float* __restrict__ frag_mean, const
   near[s] = fabs(p - threshold) <= guard ? 1 : 0;
 }
 
+// x (fp32) -> three bf16 planes with x = hi + mid + lo up to 2^-24 |x| (OPV_DTYPE_F32_TC: fp32 GEMMs as six bf16 passes
+// on the tcgen05 kernel).  Plane stride = n elements.
+__global__ void split3_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ planes, const int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    planes[i] = hi;
+    planes[n + i] = mid;
+    planes[2 * n + i] = lo;
+  }
+}
+
 }  // namespace opv

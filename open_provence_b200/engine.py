@@ -21,7 +21,20 @@ _DTYPE_ALIASES = {
     "float32": N.OPV_DTYPE_F32,
     "f32": N.OPV_DTYPE_F32,
     torch.float32: N.OPV_DTYPE_F32,
+    # fp32 parity through the tensor-core pipeline: six bf16 tcgen05 passes per projection (include/opv.h)
+    "fp32_tc": N.OPV_DTYPE_F32_TC,
+    "f32_tc": N.OPV_DTYPE_F32_TC,
 }
+
+
+def split3_bf16(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [out, in] -> bf16 [3, out, in] with w = hi + mid + lo up to 2^-24 |w| (OPV_DTYPE_F32_TC weights)."""
+    w = w.detach().to(torch.float32)
+    hi = w.to(torch.bfloat16)
+    r1 = w - hi.to(torch.float32)
+    mid = r1.to(torch.bfloat16)
+    lo = (r1 - mid.to(torch.float32)).to(torch.bfloat16)
+    return torch.stack([hi, mid, lo]).contiguous()
 
 
 def resolve_engine_dtype(dtype: Any) -> int:
@@ -106,6 +119,7 @@ class Engine:
 
         self.dtype_code = resolve_engine_dtype(dtype)
         self.op_dtype = torch.bfloat16 if self.dtype_code == N.OPV_DTYPE_BF16 else torch.float32
+        self.split_gemm = self.dtype_code == N.OPV_DTYPE_F32_TC
         self.fused = bool(fuse_epilogues) and self.dtype_code == N.OPV_DTYPE_BF16
         self.hidden = int(backbone_cfg["hidden_size"])
         self.layers = int(backbone_cfg["num_hidden_layers"])
@@ -174,15 +188,23 @@ class Engine:
             lp = f"{p}model.layers.{l}."
             lw = layers[l]
             lw.d_attn_norm = self._dev(get(lp + "attn_norm.weight"), f32).data_ptr() if l > 0 else None
-            lw.d_wqkv = self._dev(get(lp + "attn.Wqkv.weight"), op).data_ptr()
-            lw.d_wo = self._dev(get(lp + "attn.Wo.weight"), op).data_ptr()
+            def gw(t: torch.Tensor) -> int:  # GEMM weight: operand dtype, or hi | mid | lo bf16 planes
+                if self.split_gemm:
+                    return self._dev(split3_bf16(t), torch.bfloat16).data_ptr()
+                return self._dev(t, op).data_ptr()
+
+            lw.d_wqkv = gw(get(lp + "attn.Wqkv.weight"))
+            lw.d_wo = gw(get(lp + "attn.Wo.weight"))
             lw.d_mlp_norm = self._dev(get(lp + "mlp_norm.weight"), f32).data_ptr()
             wi = get(lp + "mlp.Wi.weight")
             if tuple(wi.shape) != (2 * self.inter, self.hidden):
                 raise ValueError(f"layer {l}: Wi has shape {tuple(wi.shape)}")
-            wi = wi.detach().to(dtype=op)
-            lw.d_wi = self._dev(interleave_wi(wi) if self.fused else wi, op).data_ptr()
-            lw.d_wo2 = self._dev(get(lp + "mlp.Wo.weight"), op).data_ptr()
+            if self.split_gemm:
+                lw.d_wi = gw(wi)
+            else:
+                wi = wi.detach().to(dtype=op)
+                lw.d_wi = self._dev(interleave_wi(wi) if self.fused else wi, op).data_ptr()
+            lw.d_wo2 = gw(get(lp + "mlp.Wo.weight"))
         w.h_layers = C.cast(layers, C.POINTER(N.OpvLayerWeights))
 
         cfg = N.OpvConfig()

@@ -104,6 +104,7 @@ def test_full_depth_parity(name):
 
     e16_rank, e16_prune = errs(*_engine(cfg, sd, seqs, "bf16"))
     e32_rank, e32_prune = errs(*_engine(cfg, sd, seqs, "fp32"))
+    etc_rank, etc_prune = errs(*_engine(cfg, sd, seqs, "fp32_tc"))  # fp32 through the tcgen05 GEMM pipeline (6 bf16 passes)
     try:
         r16_rank, r16_prune = errs(*_hf_bf16_gpu(cfg, sd, seqs))
     except Exception as exc:  # noqa: BLE001 -- the comparand is informational; the engine bounds below still apply
@@ -114,15 +115,17 @@ def test_full_depth_parity(name):
         "max_abs_prune_logit": s_prune, "max_abs_rank_logit": s_rank,
         "engine_bf16": {"rank": e16_rank, "prune": e16_prune, "prune_rel": e16_prune / s_prune},
         "engine_fp32": {"rank": e32_rank, "prune": e32_prune, "prune_rel": e32_prune / s_prune},
+        "engine_fp32_tc": {"rank": etc_rank, "prune": etc_prune, "prune_rel": etc_prune / s_prune},
         "reference_bf16_hf_gpu": {"rank": r16_rank, "prune": r16_prune, "prune_rel": r16_prune / s_prune},
     }
     _record(name, entry)
     print(f"{name} L={cfg['num_hidden_layers']} S={CASES[name]} |prune|max={s_prune:.1f}: "
           f"engine bf16 rank {e16_rank:.2e} prune {e16_prune:.2e} ({e16_prune / s_prune:.1e} rel) | "
-          f"engine fp32 rank {e32_rank:.2e} prune {e32_prune:.2e} | "
+          f"engine fp32 rank {e32_rank:.2e} prune {e32_prune:.2e} | fp32_tc rank {etc_rank:.2e} prune {etc_prune:.2e} | "
           f"reference bf16 (HF, GPU) rank {r16_rank:.2e} prune {r16_prune:.2e}")
     # fp32 mode: north_star's 1e-5, relative to the logit scale (|logit| ~ 40: fp32 ulp there is 4e-6)
     assert e32_rank < 1e-5 * s_rank * 4 and e32_prune < 1e-5 * s_prune
+    assert etc_rank < 1e-5 * s_rank * 4 and etc_prune < 1e-5 * s_prune
     # bf16 mode: measured bound, relative to the logit scale ...
     assert e16_prune < BF16_REL_PRUNE * s_prune and e16_rank < BF16_REL_RANK * max(s_rank, 1.0) + 2e-3
     # ... and never worse than the reference's own bf16 forward on the same inputs
