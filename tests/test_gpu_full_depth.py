@@ -7,9 +7,13 @@ pinned to the same forward (tests/test_oracle_golden.py) but needs ~80 s per 204
 Second comparand: the reference's own bf16 path (the same HF model in bf16 on the GPU, standalone:219-233,
 1597-1604), so that the engine's bf16 error is stated next to the error of the path north_star's tolerance refers to.
 
-Tolerances are the measured ones (B200, round 2), stated as absolute AND relative to the
-largest |logit| of the case.  Random-init weights with a N(0, 0.5^2) pruning head give |prune logit| up to ~50, i.e.
-one bf16 ulp of a logit is already 0.25: no bf16 implementation reaches 1e-3 absolute there.
+Tolerances are the measured ones (B200, round 2, profiles/r2i_parity_full_depth.json), stated as
+absolute AND relative to the largest |logit| of the case (random-init weights, |prune logit| up to ~6.5):
+
+    engine bf16      rank 1.1e-3 .. 2.4e-3   prune 6.4e-3 .. 8.9e-3  (1.0e-3 .. 1.4e-3 of the scale)
+    engine fp32      rank <= 3.8e-7          prune <= 9.5e-7          (FFMA kernels)
+    engine fp32_tc   rank <= 7.5e-7          prune <= 2.3e-6          (tcgen05 GEMM pipeline, 6 bf16 passes)
+    reference bf16   rank 6.0e-3 .. 2.1e-2   prune 3.8e-2 .. 5.4e-2   (HF ModernBERT bf16 on the same GPU)
 """
 
 from __future__ import annotations
@@ -39,8 +43,8 @@ CASES = {
 VOCAB = 4096  # depth, widths and head counts are the real ones; the embedding table is cut to keep the state dict small
 
 # measured bounds (relative to max |logit| of the case): bf16 engine vs fp64
-BF16_REL_PRUNE = 6e-3
-BF16_REL_RANK = 6e-3
+BF16_REL_PRUNE = 3e-3  # x max |prune logit|
+BF16_ABS_RANK = 5e-3
 
 
 def _hf_fp64(cfg, sd, seqs):
@@ -123,11 +127,11 @@ def test_full_depth_parity(name):
           f"engine bf16 rank {e16_rank:.2e} prune {e16_prune:.2e} ({e16_prune / s_prune:.1e} rel) | "
           f"engine fp32 rank {e32_rank:.2e} prune {e32_prune:.2e} | fp32_tc rank {etc_rank:.2e} prune {etc_prune:.2e} | "
           f"reference bf16 (HF, GPU) rank {r16_rank:.2e} prune {r16_prune:.2e}")
-    # fp32 mode: north_star's 1e-5, relative to the logit scale (|logit| ~ 40: fp32 ulp there is 4e-6)
-    assert e32_rank < 1e-5 * s_rank * 4 and e32_prune < 1e-5 * s_prune
-    assert etc_rank < 1e-5 * s_rank * 4 and etc_prune < 1e-5 * s_prune
+    # fp32 modes: north_star's 1e-5 (absolute; logits here reach |6.5|), FFMA kernels and tcgen05 pipeline alike
+    assert e32_rank < 1e-5 and e32_prune < 1e-5
+    assert etc_rank < 1e-5 and etc_prune < 1e-5
     # bf16 mode: measured bound, relative to the logit scale ...
-    assert e16_prune < BF16_REL_PRUNE * s_prune and e16_rank < BF16_REL_RANK * max(s_rank, 1.0) + 2e-3
+    assert e16_prune < BF16_REL_PRUNE * s_prune and e16_rank < BF16_ABS_RANK
     # ... and never worse than the reference's own bf16 forward on the same inputs
     if np.isfinite(r16_prune):
         assert e16_prune <= r16_prune * 1.05 + 1e-6
