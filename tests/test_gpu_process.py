@@ -265,3 +265,27 @@ def test_single_launch_fast_path_equals_general_path(which, model_fp32, model_bf
     assert scorer._run_single_launch(table, 0.3) is None
     again = scorer.run(table, 0.3)
     assert np.array_equal(again["keep"], slow["keep"]) and np.allclose(again["sent_prob"], slow["sent_prob"], atol=1e-12)
+
+
+def test_load_and_process_the_way_eval_mldr_does(tiny_ckpt_dir, process_golden):
+    """scripts/eval_mldr.py:145-165 (`_load_process_fn`): ``OpenProvenceModel.from_pretrained(path, device=..., max_length=...,
+    trust_remote_code=..., torch_dtype=...)`` then ``.eval()`` and the bound ``process`` called with the keyword set of
+    ``build_records`` (385-418) after the signature filter the script applies (``log_timing`` is not a parameter here
+    either way)."""
+    import inspect
+
+    model = OpenProvenceModel.from_pretrained(str(tiny_ckpt_dir), device="cuda", max_length=96, trust_remote_code=True,
+                                              torch_dtype=torch.float32)
+    assert model.eval() is model and model.max_length == 96
+    process_fn = model.process
+    kwargs = {"question": ["Which topic?", "What are bananas?"], "context": [["Sentence one is here. Sentence two follows!"],
+              ["Bananas are berries. They grow in clusters."]], "title": [[None], ["Bananas"]], "threshold": 0.25,
+              "batch_size": 4, "log_timing": False, "use_best_reranker_score": True, "show_progress": False,
+              "return_sentence_texts": True}
+    supported = set(inspect.signature(process_fn).parameters)
+    assert {"question", "context", "title", "threshold", "batch_size", "use_best_reranker_score", "show_progress",
+            "return_sentence_texts"} <= supported
+    result = process_fn(**{k: v for k, v in kwargs.items() if k in supported}, sentence_splitter=simple_sentence_splitter)
+    for key in ("pruned_context", "reranking_score", "compression_rate", "kept_sentences", "removed_sentences", "title"):
+        assert key in result and len(result[key]) == 2
+    assert all(isinstance(s, float) for row in result["reranking_score"] for s in row)
