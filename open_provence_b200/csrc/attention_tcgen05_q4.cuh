@@ -1,0 +1,332 @@
+// Global (full) self-attention on tcgen05 with FOUR 128-row query tiles in flight per SM ("q4").
+//
+// What bounds the other kernels (profiles/r2_attention_notes.md): the MUFU.EX2 unit (16 / clk / SM) is ~65 % busy
+// because each scheduler hosts only two softmax warps, and while both sit in hand-offs (barrier waits, TMEM round trips)
+// the unit idles; rows split across two threads pay an exchange per key block instead.  Here every scheduler hosts
+// FOUR softmax warps, each owning whole rows:
+//   * one CTA per SM (all 512 TMEM columns), work unit = (sequence, head, 512 query rows) = Q tiles 0..3;
+//     every K / V block is loaded once for all four (a quarter of the L2 -> smem traffic per query row);
+//   * key blocks of 64: tile j owns TMEM columns [128 j, 128 j + 128): S_j (64 fp32 columns) with P_j (32 columns of
+//     bf16 pairs) written over its first half once the scores are in registers, and O_j in the upper 64 columns;
+//   * one softmax thread per query row (warp = 4 j + lane quarter): 64 scores per block in registers, thread-local max /
+//     exp2 / sum, lazy rescale of O (threshold 2^8) -- no exchange between threads, ONE barrier wait (s_full) and one
+//     arrival (p_full) per block.  Because P aliases S, the MMA warp issues P_j(i).V(i) and THEN S_j(i+1) = Q_j.K(i+1)^T;
+//     the tensor pipe executes in order, so s_full_j(i+1) also means "O_j holds blocks <= i" and nothing else has to be
+//     waited for.  While tile j waits for that pair of MMAs, the other three tiles of the scheduler run their softmax;
+//   * two MMA issuer warps (tiles 0,1 and tiles 2,3), one thread each; one TMA producer warp; 4-stage K and V rings.
+// Sliding-window layers use attention_tcgen05_local.cuh.
+#pragma once
+
+#include <math_constants.h>
+
+#include "attention_tcgen05.cuh"
+
+namespace opv {
+
+constexpr int kQ4Threads = 640;  // warps 0..15 softmax (tile = warp / 4), 16 TMA producer, 17 / 18 MMA issuers, 19 TMEM allocation
+constexpr int kQ4Tiles = 4;
+constexpr int kQ4BlockN = 64;    // keys per block
+constexpr int kQ4Stages = 4;
+constexpr int kQ4TmemCols = 512;
+constexpr int kQ4SuperM = kQ4Tiles * kFaBlockM;   // query rows per work unit
+constexpr int kQ4KvBytes = kQ4BlockN * 64 * 2;    // one 64-key x 64-dim bf16 tile
+
+struct Q4SmemLayout {
+  static constexpr int kQ = 0;                                   // 4 x [128][64] bf16
+  static constexpr int kK = kQ + kQ4Tiles * kFaTileBytes;        // kQ4Stages x [64][64] bf16
+  static constexpr int kV = kK + kQ4Stages * kQ4KvBytes;
+  static constexpr int kBars = kV + kQ4Stages * kQ4KvBytes;
+  static constexpr int kTotal = kBars + 512 + 1024;              // + barriers + slack for the 1024 B alignment
+};
+
+// tm_q: qkv [T, 3H] with a 128-row x 64-column box (Q tiles); tm_kv: the same tensor with a 64-row box (K / V blocks)
+__global__ void __launch_bounds__(kQ4Threads, 1)
+attention_tcgen05_q4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                            __nv_bfloat16* __restrict__ out, const int32_t* __restrict__ cu_seqlens, const int H,
+                            const int n_seqs, const int supers_per_seq, const int pdl_late) {
+  using L = Q4SmemLayout;
+  constexpr int S = kQ4Stages;
+  const int heads = H / 64;
+  const int total_units = n_seqs * heads * supers_per_seq;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw0 = smem_u32(smem_raw);
+  const uint32_t sm0 = (raw0 + 1023u) & ~1023u;  // aligned in the shared address space (see attention_tcgen05_pp.cuh)
+  uint8_t* smem = smem_raw + (sm0 - raw0);
+  const uint32_t a_q = sm0 + L::kQ, a_k = sm0 + L::kK, a_v = sm0 + L::kV;
+  const uint32_t q_full = sm0 + L::kBars;     // [4]  Q_j landed                                       (TMA)
+  const uint32_t q_empty = q_full + 8 * 4;    // [4]  last S_j of a unit complete                      (tcgen05.commit)
+  const uint32_t s_full = q_empty + 8 * 4;    // [4]  S_j(i) complete (and with it P_j(i-1).V(i-1))    (tcgen05.commit)
+  const uint32_t p_full = s_full + 8 * 4;     // [4]  P_j(i) written (+ O_j rescaled)                  (4 warp arrivals)
+  const uint32_t o_full = p_full + 8 * 4;     // [4]  last P_j.V of a unit complete                    (tcgen05.commit)
+  const uint32_t o_empty = o_full + 8 * 4;    // [4]  O_j read by the epilogue                         (4 warp arrivals)
+  const uint32_t k_full = o_empty + 8 * 4;    // [S]
+  const uint32_t k_empty = k_full + 8 * S;    // [S]  both issuers' S MMAs on the stage complete       (2 x tcgen05.commit)
+  const uint32_t v_full = k_empty + 8 * S;    // [S]
+  const uint32_t v_empty = v_full + 8 * S;    // [S]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kBars + 8 * (6 * 4 + 4 * S));
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  // Unit u -> (sequence, head, 512-row query range); consecutive u are consecutive query ranges of one (sequence, head).
+  struct Unit {
+    int begin, n, q0, head, nb, tiles;  // nb key blocks of 64; tiles = active Q tiles (1..4)
+  };
+  auto decode = [&](const int u, Unit& un) -> bool {
+    const int qt = u % supers_per_seq;
+    const int sh = u / supers_per_seq;
+    const int seq = sh / heads;
+    un.head = sh - seq * heads;
+    un.begin = cu_seqlens[seq];
+    un.n = cu_seqlens[seq + 1] - un.begin;
+    un.q0 = qt * kQ4SuperM;
+    if (un.q0 >= un.n) return false;
+    un.nb = (un.n + kQ4BlockN - 1) / kQ4BlockN;
+    un.tiles = min(kQ4Tiles, (un.n - un.q0 + kFaBlockM - 1) / kFaBlockM);
+    return true;
+  };
+
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+  }
+  if (warp == 17 && lane == 0) {
+    for (int j = 0; j < kQ4Tiles; ++j) {
+      mbar_init_a(q_full + 8 * j, 1);
+      mbar_init_a(q_empty + 8 * j, 1);
+      mbar_init_a(s_full + 8 * j, 1);
+      mbar_init_a(p_full + 8 * j, 4);
+      mbar_init_a(o_full + 8 * j, 1);
+      mbar_init_a(o_empty + 8 * j, 4);
+    }
+    for (int s = 0; s < S; ++s) {
+      mbar_init_a(k_full + 8 * s, 1);
+      mbar_init_a(k_empty + 8 * s, 2);  // one tcgen05.commit per issuer
+      mbar_init_a(v_full + 8 * s, 1);
+      mbar_init_a(v_empty + 8 * s, 2);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 19) {
+    tmem_alloc(tmem_slot, kQ4TmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (!pdl_late) pdl_launch_dependents();
+  pdl_wait();  // the prologue above overlapped the previous kernel; qkv is visible from here on
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  // Register pool of the CTA = 96 (ptxas cap for 640 threads) x 640 = 61440 = 16 softmax warps x 32 x 104 + 4 x 32 x 64;
+  // setmaxnreg.inc only draws from what the CTA's own warps released.
+  if (warp >= 16) {
+    setmaxnreg_dec<64>();
+    if (warp == 16) {
+      // ------------------------------ TMA producer ------------------------------
+      if (lane == 0) {
+        uint32_t td0 = 0, td1 = 0, td2 = 0, td3 = 0, kc = 0, vc = 0;
+        Unit un;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+          if (!decode(u, un)) continue;
+          auto load_q = [&](const int j, uint32_t& td) {
+            if (j >= un.tiles) return;
+            if (td > 0) mbar_wait_a(q_empty + 8 * j, (td - 1) & 1);  // the previous unit's S_j MMAs have read Q_j
+            mbar_expect_tx_a(q_full + 8 * j, kFaTileBytes);
+            tma_load_2d_a(a_q + j * kFaTileBytes, &tm_q, q_full + 8 * j, un.head * 64, un.begin + un.q0 + j * kFaBlockM);
+            ++td;
+          };
+          load_q(0, td0);
+          load_q(1, td1);
+          load_q(2, td2);
+          load_q(3, td3);
+          for (int i = 0; i <= un.nb; ++i) {  // consumption order of the issuers: K0, K1, V0, K2, V1, ...
+            if (i < un.nb) {
+              const uint32_t sg = kc % S;
+              mbar_wait_a(k_empty + 8 * sg, ((kc / S) & 1) ^ 1);
+              mbar_expect_tx_a(k_full + 8 * sg, kQ4KvBytes);
+              tma_load_2d_a(a_k + sg * kQ4KvBytes, &tm_kv, k_full + 8 * sg, H + un.head * 64, un.begin + i * kQ4BlockN);
+              ++kc;
+            }
+            if (i >= 1) {
+              const uint32_t sg = vc % S;
+              mbar_wait_a(v_empty + 8 * sg, ((vc / S) & 1) ^ 1);
+              mbar_expect_tx_a(v_full + 8 * sg, kQ4KvBytes);
+              tma_load_2d_a(a_v + sg * kQ4KvBytes, &tm_kv, v_full + 8 * sg, 2 * H + un.head * 64,
+                            un.begin + (i - 1) * kQ4BlockN);
+              ++vc;
+            }
+          }
+        }
+      }
+    } else if ((warp == 17 || warp == 18) && elect_one()) {
+      // ------------------------------ MMA issuers: warp 17 -> tiles 0, 1; warp 18 -> tiles 2, 3 (one thread each) ----
+      constexpr uint32_t idesc_s = umma_idesc_bf16_f32(kFaBlockM, kQ4BlockN);     // Q.K^T: both K-major, N = 64 keys
+      constexpr uint32_t idesc_o = umma_idesc_bf16_f32_bmn(kFaBlockM, 64);        // P.V: V is MN-major
+      const int j0 = 2 * (warp - 17);
+      uint32_t td_a = 0, td_b = 0, sc_a = 0, sc_b = 0, kc = 0, vc = 0;  // per-tile unit / block counts -> parities
+      Unit un;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        if (!decode(u, un)) continue;
+        const int nb = un.nb;
+        for (int i = 0; i <= nb; ++i) {
+          uint32_t v_addr = 0, k_addr = 0, sg_k = 0, sg_v = 0;
+          // the waits also keep this issuer from arriving on k_empty / v_empty for the NEXT use of a stage before the
+          // other issuer has arrived for this one (two arrivals complete a phase)
+          if (i >= 1) {
+            sg_v = vc % S;
+            mbar_wait_a(v_full + 8 * sg_v, (vc / S) & 1);
+            v_addr = a_v + sg_v * kQ4KvBytes;
+          }
+          if (i < nb) {
+            sg_k = kc % S;
+            mbar_wait_a(k_full + 8 * sg_k, (kc / S) & 1);
+            k_addr = a_k + sg_k * kQ4KvBytes;
+          }
+          auto step = [&](const int j, const uint32_t td, uint32_t& sc) {
+            if (j >= un.tiles) return;
+            const uint32_t t_s = tmem_base + j * 128, t_o = t_s + 64;
+            if (i >= 1) {  // O_j (+)= P_j(i-1) . V(i-1); P_j lives in the first 32 columns of S_j
+              mbar_wait_a(p_full + 8 * j, (sc - 1) & 1);
+              if (i == 1 && td > 0) mbar_wait_a(o_empty + 8 * j, (td - 1) & 1);  // epilogue has read the previous O_j
+              tc_fence_after();
+#pragma unroll
+              for (int k = 0; k < 4; ++k)  // 16 keys per MMA: two 8-key groups of 1024 B
+                umma_bf16_ts(t_o, t_s + k * 8, umma_desc_mn_sw128(v_addr + k * 2048), idesc_o, (i > 1 || k > 0) ? 1u : 0u);
+              if (i == nb) umma_commit_a(o_full + 8 * j);
+            }
+            if (i < nb) {  // S_j(i) = Q_j . K(i)^T, issued AFTER P_j(i-1).V(i-1): it overwrites P_j(i-1)
+              if (i == 0) mbar_wait_a(q_full + 8 * j, td & 1);
+              tc_fence_after();
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss(t_s, umma_desc_k_sw128(a_q + j * kFaTileBytes + k * 32), umma_desc_k_sw128(k_addr + k * 32),
+                             idesc_s, k != 0 ? 1u : 0u);
+              umma_commit_a(s_full + 8 * j);
+              if (i == nb - 1) umma_commit_a(q_empty + 8 * j);
+              ++sc;
+            }
+          };
+          step(j0, td_a, sc_a);
+          step(j0 + 1, td_b, sc_b);
+          if (i >= 1) {
+            umma_commit_a(v_empty + 8 * sg_v);
+            ++vc;
+          }
+          if (i < nb) {
+            umma_commit_a(k_empty + 8 * sg_k);
+            ++kc;
+          }
+        }
+        if (j0 < un.tiles) ++td_a;
+        if (j0 + 1 < un.tiles) ++td_b;
+      }
+    }
+  } else {
+    // ------------------------------ softmax warps: one thread per query row, four tiles ----
+    setmaxnreg_inc<104>();
+    const int j = warp >> 2, quarter = warp & 3;
+    const int r_tile = quarter * 32 + lane;  // row inside the tile == TMEM lane
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + j * 128;  // S_j: 64 columns; P_j: first 32
+    const uint32_t t_o = t_s + 64;                                                           // O_j: 64 columns
+    const uint32_t my_s_full = s_full + 8 * j, my_p_full = p_full + 8 * j, my_o_full = o_full + 8 * j,
+                   my_o_empty = o_empty + 8 * j;
+    const float scale_log2 = 0.125f * 1.44269504088896340736f;  // head_dim^-0.5 * log2(e)
+    uint32_t bc = 0, done = 0;  // running counts of this tile's key blocks / units -> barrier parities
+    Unit un;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      if (!decode(u, un)) continue;
+      if (j >= un.tiles) continue;
+      const int n = un.n, nb = un.nb;
+      const int row = un.q0 + j * kFaBlockM + r_tile;  // row inside the sequence
+      float m_run = -CUDART_INF_F, l_run = 0.f;
+
+      for (int i = 0; i < nb; ++i, ++bc) {
+        mbar_wait_a(my_s_full, bc & 1);  // S_j(i) complete; O_j holds blocks < i (the tensor pipe runs in order)
+        tc_fence_after();
+        uint32_t sr[64];
+        tmem_ld_32x32b_x64(t_s, sr);
+        const int valid = n - i * kQ4BlockN;  // keys of this block inside the sequence (the last block may be partial)
+        if (valid < kQ4BlockN) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (c >= valid) sr[c] = 0xff800000u;  // -inf
+        }
+        float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) {
+          mx0 = fmax3(mx0, __uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7]));
+        }
+        const float m_cand = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);  // finite: key 0 is valid
+        const bool upd = (m_cand - m_run) > kFaRescaleThreshold;
+        const float m_new = upd ? m_cand : m_run;
+        const float corr = upd ? ex2_approx(m_run - m_new) : 1.0f;
+        m_run = m_new;
+        if (i > 0 && __any_sync(0xffffffffu, upd)) {  // lazy rescale of O_j, 32 columns at a time (rare)
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t orr[32];
+            tmem_ld_32x32_raw(t_o + 32 * hlf, orr);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) orr[c] = __float_as_uint(__uint_as_float(orr[c]) * corr);
+            tmem_st_32x32b_x32(t_o + 32 * hlf, orr);
+          }
+        }
+        // exponentials: packed fp32 pairs (FFMA2 / FADD2), probabilities packed to bf16 pairs
+        float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
+        const float2 sc2 = make_float2(scale_log2, scale_log2), nm2 = make_float2(-m_new, -m_new);
+        uint32_t pr[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1])), sc2, nm2);
+          const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(sr[2 * c + 2]), __uint_as_float(sr[2 * c + 3])), sc2, nm2);
+          const float2 p01 = make_float2(ex2_approx(x01.x), ex2_approx(x01.y));
+          const float2 p23 = make_float2(ex2_approx(x23.x), ex2_approx(x23.y));
+          acc01 = __fadd2_rn(acc01, p01);
+          acc23 = __fadd2_rn(acc23, p23);
+          pr[c] = pack_bf16x2(p01.x, p01.y);
+          pr[c + 1] = pack_bf16x2(p23.x, p23.y);
+        }
+        const float2 acc = __fadd2_rn(acc01, acc23);
+        l_run = l_run * corr + (acc.x + acc.y);
+        tmem_st_32x32b_x32(t_s, pr);  // P_j(i) over the first half of S_j(i): every score of this row is in registers
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(my_p_full);
+      }
+
+      // epilogue: O / l -> bf16 -> out[begin + row, head*64 : head*64+64]
+      mbar_wait_a(my_o_full, done & 1);
+      tc_fence_after();
+      uint32_t orr[64];
+      tmem_ld_32x32b_x64(t_o, orr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(my_o_empty);  // the next unit's first P_j.V may overwrite O_j
+      if (row < n) {
+        const float inv = 1.0f / l_run;
+        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(un.begin) + row) * H + un.head * 64);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(orr[8 * g + 0]) * inv, __uint_as_float(orr[8 * g + 1]) * inv);
+          v.y = pack_bf16x2(__uint_as_float(orr[8 * g + 2]) * inv, __uint_as_float(orr[8 * g + 3]) * inv);
+          v.z = pack_bf16x2(__uint_as_float(orr[8 * g + 4]) * inv, __uint_as_float(orr[8 * g + 5]) * inv);
+          v.w = pack_bf16x2(__uint_as_float(orr[8 * g + 6]) * inv, __uint_as_float(orr[8 * g + 7]) * inv);
+          dst[g] = v;
+        }
+      }
+      ++done;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 19) tmem_dealloc(tmem_base, kQ4TmemCols);
+}
+
+}  // namespace opv

@@ -17,6 +17,7 @@
 #include "attention_tcgen05.cuh"
 #include "attention_tcgen05_local.cuh"
 #include "attention_tcgen05_pp.cuh"
+#include "attention_tcgen05_q4.cuh"
 #include "attention_tcgen05_v3.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -106,6 +107,7 @@ struct Options {
   // 4 = one-thread-per-row (P in TMEM, 2 CTAs / SM) everywhere, 5 = two-Q-tile kernel (1 CTA / SM) everywhere,
   // 6 = one-pass sliding-window kernel (window <= 128; what 1 uses for such layers)
   int attention_impl = 1;
+  int attention_q4 = 0;                  // 1 = attention_impl 1 runs global layers on the four-Q-tile kernel
   int attention_debug = 0;               // timing experiments of the two-Q-tile kernel (attention_tcgen05_pp.cuh), 0 = off
   long long* attention_trace = nullptr;  // device buffer for clock64() stamps (tools/attn_check.py); nullptr in the product
   // bf16 GEMM with N % 256 == 0: 1 = CTA-pair kernel (cta_group::2, 256 x 256 tiles), 0 = single-CTA kernel
@@ -205,6 +207,8 @@ int ensure_device_setup() {
                                   opv::FaSmemLayout<false>::kTotal));
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   opv::Fa3SmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_q4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::Q4SmemLayout::kTotal));
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_local_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   opv::LoSmemLayout::kTotal));
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_pp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -380,13 +384,27 @@ int launch_final_prune(const float* h, const float* w, const float* wp, const fl
 
 // tm_qkv: TMA map of the packed qkv [T, 3H] buffer with a 128-row x 64-column box (tcgen05 kernels only)
 int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, int n_seqs, int max_seqlen, int heads,
-                     int half_window, const CUtensorMap* tm_qkv, cudaStream_t s) {
+                     int half_window, const CUtensorMap* tm_qkv, const CUtensorMap* tm_qkv64, cudaStream_t s) {
   if (n_seqs <= 0 || max_seqlen <= 0) return OPV_OK;
   if (n_seqs > 65535) return fail(OPV_ERR_UNSUPPORTED, "at most 65535 sequences per launch");
   const int H = heads * 64;
   if (dtype == OPV_DTYPE_BF16) {
     if (!tm_qkv) return fail(OPV_ERR_INVALID_ARGUMENT, "tcgen05 attention needs the qkv tensor map");
     const int impl = t_opt.attention_impl;
+    if (impl == 7 && half_window >= 0)
+      return fail(OPV_ERR_UNSUPPORTED, "attention_impl 7 (four-Q-tile kernel) implements global attention only");
+    if (impl == 7 || (impl == 1 && half_window < 0 && t_opt.attention_q4)) {
+      // global layers: ONE CTA per SM, four 128-row query tiles in flight, 64-key blocks (attention_tcgen05_q4.cuh)
+      if (!tm_qkv64) return fail(OPV_ERR_INVALID_ARGUMENT, "the four-Q-tile attention kernel needs the 64-row qkv tensor map");
+      const int supers_per_seq = (max_seqlen + opv::kQ4SuperM - 1) / opv::kQ4SuperM;
+      const int64_t total = static_cast<int64_t>(n_seqs) * heads * supers_per_seq;
+      if (total > 0x7fffffffLL) return fail(OPV_ERR_UNSUPPORTED, "too many attention tiles for one launch");
+      const int grid = static_cast<int>(total < g_num_sms ? total : g_num_sms);
+      launch_pdl(opv::attention_tcgen05_q4_kernel, dim3(grid), dim3(opv::kQ4Threads), opv::Q4SmemLayout::kTotal, s,
+                 *tm_qkv, *tm_qkv64, static_cast<__nv_bfloat16*>(out), cu, H, n_seqs, supers_per_seq, pdl_late_flag());
+      OPV_LAUNCH_CHECK("attention_tcgen05_q4_kernel");
+      return OPV_OK;
+    }
     if (impl == 5) {
       // persistent, ONE CTA per SM: (sequence, head, 256-query super tile) list with a grid stride, two Q tiles in flight
       const int supers_per_seq = (max_seqlen + opv::kPpSuperM - 1) / opv::kPpSuperM;
@@ -450,8 +468,10 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int set_option_in(Options& o, const char* name, int64_t value) {
   if (strcmp(name, "attention_impl") == 0) {
-    if (value < 1 || value > 6) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_impl must be 1 .. 6");
+    if (value < 1 || value > 7) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_impl must be 1 .. 7");
     o.attention_impl = static_cast<int>(value);
+  } else if (strcmp(name, "attention_q4") == 0) {
+    o.attention_q4 = value != 0;
   } else if (strcmp(name, "attention_debug") == 0) {
     if (value < 0 || value > 4) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_debug must be 0 .. 4");
     o.attention_debug = static_cast<int>(value);
@@ -501,7 +521,7 @@ struct opv_engine {
     const void* ws = nullptr;
     int64_t tokens = -1;
     uint64_t stamp = 0;
-    CUtensorMap x, attn, act, qkv, h, u;
+    CUtensorMap x, attn, act, qkv, qkv64, h, u;
   };
   ActMaps act_maps[4];
   uint64_t act_maps_clock = 0;
@@ -729,7 +749,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
   if (c.dtype == OPV_DTYPE_BF16) {
     using bf16 = __nv_bfloat16;
     const bool fused = c.fuse_epilogues != 0;
-    CUtensorMap tm_x, tm_attn, tm_act, tm_qkv, tm_h, tm_u;
+    CUtensorMap tm_x, tm_attn, tm_act, tm_qkv, tm_qkv64, tm_h, tm_u;
     {
       std::lock_guard<std::mutex> lock(e->mu);
       opv_engine::ActMaps* slot = nullptr;
@@ -742,6 +762,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
         slot = victim;
         slot->tokens = -1;  // invalid until every map below is encoded
         if ((rc = make_tmap_bf16(&slot->qkv, qkv, T, 3 * H, opv::kFaBlockM))) return rc;  // GEMM store + attention loads
+        if ((rc = make_tmap_bf16(&slot->qkv64, qkv, T, 3 * H, opv::kQ4BlockN))) return rc;  // 64-key K / V blocks
         if ((rc = make_tmap_2d(&slot->h, h, true, T, H, opv::kGemmBlockM))) return rc;     // residual reduce-add
         if (!fused && (rc = make_tmap_bf16(&slot->u, u, T, 2 * I, opv::kGemmBlockM))) return rc;
         if ((rc = make_tmap_bf16(&slot->x, x, T, H, opv::kGemmBlockM))) return rc;
@@ -751,7 +772,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
         slot->tokens = T;
       }
       slot->stamp = ++e->act_maps_clock;
-      tm_x = slot->x, tm_attn = slot->attn, tm_act = slot->act, tm_qkv = slot->qkv, tm_h = slot->h, tm_u = slot->u;
+      tm_x = slot->x, tm_attn = slot->attn, tm_act = slot->act, tm_qkv = slot->qkv, tm_qkv64 = slot->qkv64, tm_h = slot->h, tm_u = slot->u;
     }
     {
       LaunchScope sc(e, stream, OPV_PROF_EMBED);
@@ -784,7 +805,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       {
         LaunchScope sc(e, stream, global ? OPV_PROF_ATTN_GLOBAL : OPV_PROF_ATTN_LOCAL);
         rc = launch_attention(OPV_DTYPE_BF16, qkv, attn, d_cu_seqlens, n_seqs, max_seqlen, heads,
-                              global ? -1 : half_window, &tm_qkv, stream);
+                              global ? -1 : half_window, &tm_qkv, &tm_qkv64, stream);
       }
       if (rc) return rc;
       opv::GemmEpilogueArgs er{};
@@ -878,7 +899,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       {
         LaunchScope sc(e, stream, global ? OPV_PROF_ATTN_GLOBAL : OPV_PROF_ATTN_LOCAL);
         rc = launch_attention(OPV_DTYPE_F32, qf, af, d_cu_seqlens, n_seqs, max_seqlen, heads,
-                              global ? -1 : half_window, nullptr, stream);
+                              global ? -1 : half_window, nullptr, nullptr, stream);
       }
       if (rc) return rc;
       {
@@ -1067,14 +1088,15 @@ int opv_op_attention(int32_t dtype, const void* d_qkv, void* d_out, const int32_
   if (!d_qkv || !d_out || !d_cu_seqlens) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_op_attention: null buffer");
   if (int rc = ensure_device_setup()) return rc;
   t_opt = defaults_snapshot();
-  CUtensorMap tm_qkv;
+  CUtensorMap tm_qkv, tm_qkv64;
   const bool tc = dtype == OPV_DTYPE_BF16;
   if (tc) {
     if (n_tokens <= 0) return OPV_OK;
     if (int rc = make_tmap_bf16(&tm_qkv, d_qkv, n_tokens, 3 * num_heads * 64, opv::kFaBlockM)) return rc;
+    if (int rc = make_tmap_bf16(&tm_qkv64, d_qkv, n_tokens, 3 * num_heads * 64, opv::kQ4BlockN)) return rc;
   }
   return launch_attention(dtype, d_qkv, d_out, d_cu_seqlens, n_seqs, max_seqlen, num_heads, half_window,
-                          tc ? &tm_qkv : nullptr, static_cast<cudaStream_t>(stream_));
+                          tc ? &tm_qkv : nullptr, tc ? &tm_qkv64 : nullptr, static_cast<cudaStream_t>(stream_));
 }
 
 int opv_set_option(const char* name, int64_t value) {

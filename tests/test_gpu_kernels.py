@@ -220,6 +220,29 @@ def test_attention_bf16_impls(impl, half_window):
     assert err < tol, f"attention impl={impl} window={half_window}: max err {err:.3e} (tol {tol:.3e})"
 
 
+@pytest.mark.parametrize("lengths", [[1, 2, 63, 64, 65, 127, 128, 129, 130, 200, 257, 513], [1100, 2048, 511, 512, 640], [4097]])
+def test_attention_global_four_q_tiles(lengths):
+    """Four-Q-tile kernel (attention_impl 7): 512-row work units, 64-key blocks, P aliased onto S; ragged lengths that
+    leave 1..4 tiles active and end inside a key block."""
+    heads = 3
+    g = torch.Generator().manual_seed(23)
+    qkv = (torch.randn((sum(lengths), 3 * heads * 64), generator=g) * 1.5).to(torch.bfloat16).to(DEV)
+    cu = torch.tensor([0] + list(np.cumsum(lengths)), dtype=torch.int32, device=DEV)
+    ops.set_option("attention_impl", 7)
+    try:
+        out = ops.attention(qkv, cu, max(lengths), heads, -1)
+        torch.cuda.synchronize()
+        with pytest.raises(NotImplementedError, match="global attention only"):
+            ops.attention(qkv, cu, max(lengths), heads, 64)
+    finally:
+        ops.set_option("attention_impl", 1)
+    ref = _attention_ref(qkv, lengths, heads, -1)
+    err = (out.double() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all()
+    tol = 6e-3 * max(1.0, ref.abs().max().item())
+    assert err < tol, f"four-Q-tile attention lengths={lengths}: max err {err:.3e} (tol {tol:.3e})"
+
+
 @pytest.mark.parametrize("half_window", [64, 8, 1, 0, 33])
 def test_attention_local_onepass(half_window):
     """One-pass sliding-window kernel (window <= 128): the whole band of a 128-query tile in one 256-key score tile."""
