@@ -128,10 +128,14 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
 /* Tuning switches (tests, profiling).  opv_set_option() edits the process-wide DEFAULTS: every engine snapshots them
  * at opv_create(), the single-op entry points (opv_op_*) read them at call time; opv_engine_set_option() changes one
  * engine only (everything except "gemm_pair", which is fixed at creation).  Both are thread-safe.
- * "attention_impl": bf16 attention kernel, 1 = default (one softmax thread per query row, two CTAs per SM, for global
- * layers; the one-pass kernel for sliding-window layers with window <= 128, two threads per row for wider windows), 2 = one thread per row with P staged through shared memory,
+ * "attention_impl": bf16 attention kernel, 1 = default (the four-Q-tile kernel for global layers -- "attention_q4" = 0
+ * puts them back on the 2-CTAs-per-SM kernel --; the one-pass kernel for sliding-window layers with window <= 128, two
+ * threads per row for wider windows), 2 = one thread per row with P staged through shared memory,
  * 3 = two threads per row everywhere, 4 = one thread per row everywhere, 5 = two-Q-tile kernel (one CTA per SM, 16
- * softmax warps, K / V shared by two query tiles) everywhere, 6 = one-pass sliding-window kernel (window <= 128).  "attention_trace_ptr": device buffer for the clock64() timeline of
+ * softmax warps, K / V shared by two query tiles) everywhere, 6 = one-pass sliding-window kernel (window <= 128), 7 = four-Q-tile kernel (one CTA per SM, four 128-row query
+ * tiles in flight, 64-key blocks; global attention only).  "attention_q4_poly": the four-Q-tile kernel computes every n-th
+ * pair of probabilities with a degree-3 polynomial on the FMA pipe instead of MUFU.EX2 (0 = none, default 6; relative
+ * error 7.5e-5, far below the bf16 rounding of the probabilities).  "attention_trace_ptr": device buffer for the clock64() timeline of
  * tools/attn_check.py (0 = off, the product setting).  "gemm_pair": 1 = CTA-pair (cta_group::2) GEMM for 256-wide
  * tiles (default), 0 = single-CTA kernel.  "gemm_group_rows": row-grouped tile order of the RoPE GEMM (default 1).
  * "pdl": 1 = GEMM / attention / LayerNorm kernels are launched with programmatic stream serialization so that each

@@ -39,7 +39,26 @@ struct Q4SmemLayout {
   static constexpr int kTotal = kBars + 512 + 1024;              // + barriers + slack for the 1024 B alignment
 };
 
-// tm_q: qkv [T, 3H] with a 128-row x 64-column box (Q tiles); tm_kv: the same tensor with a 64-row box (K / V blocks)
+// 2^x for a pair of fp32 values on the FMA / ALU pipes instead of MUFU.EX2 (Cody-Waite split + degree-3 minimax
+// polynomial on [-0.5, 0.5], relative error 7.5e-5 -- 25 x below the bf16 rounding of the probability): round(x) through
+// the 1.5 * 2^23 magic constant, f = x - round(x), p(f), exponent add as (bits << 23) + p (one LEA).  x must be <= ~100;
+// x < -125 is clamped (the result 2^-125 is as good as the 0 the MUFU path flushes to).
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float2 xc = make_float2(fmaxf(x.x, -125.f), fmaxf(x.y, -125.f));
+  const float2 t = __fadd2_rn(xc, make_float2(12582912.f, 12582912.f));
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), xc);
+  float2 p = make_float2(0.05517164617776871f, 0.05517164617776871f);
+  p = __ffma2_rn(p, f, make_float2(0.2426111251115799f, 0.2426111251115799f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  return make_float2(__int_as_float((__float_as_int(t.x) << 23) + __float_as_int(p.x)),
+                     __int_as_float((__float_as_int(t.y) << 23) + __float_as_int(p.y)));
+}
+
+// tm_q: qkv [T, 3H] with a 128-row x 64-column box (Q tiles); tm_kv: the same tensor with a 64-row box (K / V blocks).
+// POLY = n > 0: every n-th pair of probabilities of a row is computed by exp2_poly2 instead of two MUFU.EX2.
+template <int POLY>
 __global__ void __launch_bounds__(kQ4Threads, 1)
 attention_tcgen05_q4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                             __nv_bfloat16* __restrict__ out, const int32_t* __restrict__ cu_seqlens, const int H,
@@ -284,8 +303,9 @@ attention_tcgen05_q4_kernel(const __grid_constant__ CUtensorMap tm_q, const __gr
         for (int c = 0; c < 32; c += 2) {
           const float2 x01 = __ffma2_rn(make_float2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1])), sc2, nm2);
           const float2 x23 = __ffma2_rn(make_float2(__uint_as_float(sr[2 * c + 2]), __uint_as_float(sr[2 * c + 3])), sc2, nm2);
-          const float2 p01 = make_float2(ex2_approx(x01.x), ex2_approx(x01.y));
-          const float2 p23 = make_float2(ex2_approx(x23.x), ex2_approx(x23.y));
+          // pair index inside the row: c (x01) and c + 1 (x23)
+          const float2 p01 = (POLY > 0 && c % POLY == POLY - 1) ? exp2_poly2(x01) : make_float2(ex2_approx(x01.x), ex2_approx(x01.y));
+          const float2 p23 = (POLY > 0 && (c + 1) % POLY == POLY - 1) ? exp2_poly2(x23) : make_float2(ex2_approx(x23.x), ex2_approx(x23.y));
           acc01 = __fadd2_rn(acc01, p01);
           acc23 = __fadd2_rn(acc23, p23);
           pr[c] = pack_bf16x2(p01.x, p01.y);

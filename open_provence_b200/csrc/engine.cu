@@ -102,12 +102,17 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t co
 // defaults at call time.  Nothing below reads a process-global while launching: each extern "C" entry point copies
 // the options of ITS engine (or the defaults) and the SM count of the CURRENT device into thread-local state.
 struct Options {
-  // bf16 attention kernel: 1 = default (one-thread-per-row kernel for global layers; one-pass kernel for sliding-window
+  // bf16 attention kernel: 1 = default (four-Q-tile kernel for global layers; one-pass kernel for sliding-window
   // layers with window <= 128, two-threads-per-row kernel for wider windows), 2 = one-thread-per-row with P in smem, 3 = two-threads-per-row everywhere,
   // 4 = one-thread-per-row (P in TMEM, 2 CTAs / SM) everywhere, 5 = two-Q-tile kernel (1 CTA / SM) everywhere,
-  // 6 = one-pass sliding-window kernel (window <= 128; what 1 uses for such layers)
+  // 6 = one-pass sliding-window kernel (window <= 128; what 1 uses for such layers), 7 = four-Q-tile kernel (global
+  // layers only; what 1 uses for them)
   int attention_impl = 1;
-  int attention_q4 = 0;                  // 1 = attention_impl 1 runs global layers on the four-Q-tile kernel
+  int attention_q4 = 1;                  // 1 = attention_impl 1 runs global layers on the four-Q-tile kernel (default), 0 = on the 2-CTA kernel
+  // four-Q-tile kernel: every n-th probability pair of a row on the FMA pipe (exp2_poly2) instead of MUFU.EX2; 0 = none.
+  // 64 x 2048 x 8 heads, per global layer: 0 -> 0.645 ms, 16 / 12 -> 0.623, 8 -> 0.606, 6 -> 0.604, 4 -> 0.619, 3 -> 0.622,
+  // 2 -> 0.698 (issue-bound); in situ 6.04 -> 5.71 ms per step with 6.
+  int attention_q4_poly = 6;
   int attention_debug = 0;               // timing experiments of the two-Q-tile kernel (attention_tcgen05_pp.cuh), 0 = off
   long long* attention_trace = nullptr;  // device buffer for clock64() stamps (tools/attn_check.py); nullptr in the product
   // bf16 GEMM with N % 256 == 0: 1 = CTA-pair kernel (cta_group::2, 256 x 256 tiles), 0 = single-CTA kernel
@@ -207,7 +212,21 @@ int ensure_device_setup() {
                                   opv::FaSmemLayout<false>::kTotal));
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   opv::Fa3SmemLayout::kTotal));
-    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_q4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_q4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::Q4SmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_q4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::Q4SmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_q4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::Q4SmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_q4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::Q4SmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_q4_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::Q4SmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_q4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::Q4SmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_q4_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::Q4SmemLayout::kTotal));
+    OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_q4_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   opv::Q4SmemLayout::kTotal));
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_local_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   opv::LoSmemLayout::kTotal));
@@ -400,8 +419,19 @@ int launch_attention(int dtype, const void* qkv, void* out, const int32_t* cu, i
       const int64_t total = static_cast<int64_t>(n_seqs) * heads * supers_per_seq;
       if (total > 0x7fffffffLL) return fail(OPV_ERR_UNSUPPORTED, "too many attention tiles for one launch");
       const int grid = static_cast<int>(total < g_num_sms ? total : g_num_sms);
-      launch_pdl(opv::attention_tcgen05_q4_kernel, dim3(grid), dim3(opv::kQ4Threads), opv::Q4SmemLayout::kTotal, s,
-                 *tm_qkv, *tm_qkv64, static_cast<__nv_bfloat16*>(out), cu, H, n_seqs, supers_per_seq, pdl_late_flag());
+      auto* kernel = opv::attention_tcgen05_q4_kernel<0>;
+      switch (t_opt.attention_q4_poly) {  // every n-th probability pair on the FMA pipe instead of MUFU.EX2
+        case 2: kernel = opv::attention_tcgen05_q4_kernel<2>; break;
+        case 3: kernel = opv::attention_tcgen05_q4_kernel<3>; break;
+        case 4: kernel = opv::attention_tcgen05_q4_kernel<4>; break;
+        case 6: kernel = opv::attention_tcgen05_q4_kernel<6>; break;
+        case 8: kernel = opv::attention_tcgen05_q4_kernel<8>; break;
+        case 12: kernel = opv::attention_tcgen05_q4_kernel<12>; break;
+        case 16: kernel = opv::attention_tcgen05_q4_kernel<16>; break;
+        default: break;
+      }
+      launch_pdl(kernel, dim3(grid), dim3(opv::kQ4Threads), opv::Q4SmemLayout::kTotal, s, *tm_qkv, *tm_qkv64,
+                 static_cast<__nv_bfloat16*>(out), cu, H, n_seqs, supers_per_seq, pdl_late_flag());
       OPV_LAUNCH_CHECK("attention_tcgen05_q4_kernel");
       return OPV_OK;
     }
@@ -472,6 +502,10 @@ int set_option_in(Options& o, const char* name, int64_t value) {
     o.attention_impl = static_cast<int>(value);
   } else if (strcmp(name, "attention_q4") == 0) {
     o.attention_q4 = value != 0;
+  } else if (strcmp(name, "attention_q4_poly") == 0) {
+    if (value != 0 && value != 2 && value != 3 && value != 4 && value != 6 && value != 8 && value != 12 && value != 16)
+      return fail(OPV_ERR_INVALID_ARGUMENT, "attention_q4_poly must be 0, 2, 3, 4, 6, 8, 12 or 16");
+    o.attention_q4_poly = static_cast<int>(value);
   } else if (strcmp(name, "attention_debug") == 0) {
     if (value < 0 || value > 4) return fail(OPV_ERR_INVALID_ARGUMENT, "attention_debug must be 0 .. 4");
     o.attention_debug = static_cast<int>(value);

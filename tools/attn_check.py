@@ -19,6 +19,8 @@ dev = torch.device("cuda:0")
 ops.set_option("attention_impl", impl)
 import os
 dbg = int(os.environ.get("ATTN_DEBUG", "0"))
+if os.environ.get("ATTN_Q4_POLY"):
+    ops.set_option("attention_q4_poly", int(os.environ["ATTN_Q4_POLY"]))
 
 
 def ref_attention(qkv, lengths, heads, half_window):
