@@ -17,7 +17,7 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tcgen05 -s 12 -c 4 \
       -f -o "$OUT/prof_gemm" python bench.py --steps 1 --warmup 3 --no-cpu-baseline > "$OUT/ncu_gemm.log" 2>&1
   echo "== ncu full: attention"
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention -s 3 -c 3 \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention -s 3 -c 4 \
       -f -o "$OUT/prof_attn" python bench.py --steps 1 --warmup 3 --no-cpu-baseline > "$OUT/ncu_attn.log" 2>&1
 fi
 ls -la "$OUT"

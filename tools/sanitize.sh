@@ -6,6 +6,6 @@ compute-sanitizer --tool memcheck --print-limit 5 python -c "import __graft_entr
 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_families.py -m gpu -x -q -k "xsmall and bf16" 2>&1 | tail -4
 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_forward.py -m gpu -x -q -k "mean" 2>&1 | tail -4
 # round 2: one-pass sliding-window kernel, two-Q-tile kernel, fp32 through the tcgen05 GEMM pipeline (6 passes + split)
-compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "local_onepass or (attention_bf16_impls and 5-)" 2>&1 | tail -4
+compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "local_onepass or four_q_tiles or (attention_bf16_impls and 5-)" 2>&1 | tail -4
 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_forward.py -m gpu -x -q -k "tensor_core_pipeline" 2>&1 | tail -4
 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "local_onepass and 64" 2>&1 | tail -6
