@@ -138,6 +138,8 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
  * error 7.5e-5, far below the bf16 rounding of the probabilities).  "attention_trace_ptr": device buffer for the clock64() timeline of
  * tools/attn_check.py (0 = off, the product setting).  "gemm_pair": 1 = CTA-pair (cta_group::2) GEMM for 256-wide
  * tiles (default), 0 = single-CTA kernel.  "gemm_group_rows": row-grouped tile order of the RoPE GEMM (default 1).
+ * "ln_fuse": 1 = large bf16 forwards run each LayerNorm inside the residual GEMM that completes its rows (bit-identical
+ * results; measured slower on B200 because the re-reads miss L2, so default 0 = standalone LayerNorm launches).
  * "pdl": 1 = GEMM / attention / LayerNorm kernels are launched with programmatic stream serialization so that each
  * kernel's prologue overlaps its predecessor's tail (default), 0 = plain stream order; "pdl_max_tokens": forwards
  * with more packed tokens than this do not release their dependents early (default 32768, profiles/r1t_pdl.md);

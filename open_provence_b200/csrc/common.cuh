@@ -251,6 +251,12 @@ __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// at most N of the calling thread's most recent bulk groups may still be in flight; older ones are COMPLETE (their
+// writes / reductions performed), not merely done reading shared memory
+template <int N>
+__device__ __forceinline__ void tma_store_wait_complete() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM

@@ -119,6 +119,11 @@ struct Options {
   int gemm_pair = 1;
   // ROPE GEMM: 1 = a cluster finishes all column tiles of a row block before the next row block (cos|sin staged once)
   int gemm_group_rows = 1;
+  // 1 = bf16 forwards with at least one 256-row block per CTA pair run every LayerNorm but the first and the last inside
+  // the residual GEMM that completes its input rows (RESIDUAL_LN, gemm_tcgen05.cuh: four extra warps normalise a row
+  // block once its reduce-adds are complete); 0 = standalone layernorm_kernel launches (default).  Bit-identical
+  // results; measured 2122-2204 against 2221-2260 pairs/s (the re-reads miss L2, see gemm_tcgen05.cuh), so off.
+  int ln_fuse = 0;
   // 1 = the kernels that call pdl_wait() (GEMMs, attention, LayerNorm family) are launched with programmatic stream
   // serialization, so each one's prologue overlaps its predecessor's tail; 0 = plain stream order
   int pdl = 1;
@@ -206,6 +211,7 @@ int ensure_device_setup() {
     if (int rc = set_gemm_pair_attr<opv::kEpiRope>()) return rc;
     if (int rc = set_gemm_pair_attr<opv::kEpiResidual>()) return rc;
     if (int rc = set_gemm_pair_attr<opv::kEpiGeglu>()) return rc;
+    if (int rc = set_gemm_pair_attr<opv::kEpiResidualLn>()) return rc;
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   opv::FaSmemLayout<true>::kTotal));
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -292,6 +298,7 @@ int launch_gemm_pair(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUt
   const int clusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
   opv::GemmEpilogueArgs ep_launch = ep;
   ep_launch.group_rows = (EPI == opv::kEpiRope && t_opt.gemm_group_rows && pairs_m >= 4 * clusters) ? 1 : 0;
+  if (EPI == opv::kEpiResidualLn) ep_launch.group_rows = 1;  // the LayerNorm needs a row block's column tiles in one CTA pair
   ep_launch.pdl_late = pdl_late_flag();
   launch_pdl(opv::gemm_bf16_tcgen05_pair_kernel<EPI>, dim3(2 * clusters), dim3(opv::gemm_threads(EPI)),
              opv::GemmPairSmemLayout<EPI>::kTotal, stream, tm_a, tm_b, tm_c, ep_launch, (int)M, N, K);
@@ -322,6 +329,10 @@ int gemm_bf16(int epi, bool pair, const CUtensorMap& tm_a, const CUtensorMap& tm
       case opv::kEpiRope: return launch_gemm_pair<opv::kEpiRope>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
       case opv::kEpiResidual: return launch_gemm_pair<opv::kEpiResidual>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
       case opv::kEpiGeglu: return launch_gemm_pair<opv::kEpiGeglu>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
+      case opv::kEpiResidualLn:
+        if (N > 1024 || !ep.ln_w || !ep.ln_r || !ep.ln_x)
+          return fail(OPV_ERR_INVALID_ARGUMENT, "RESIDUAL_LN epilogue needs N in {256,512,768,1024} and the LayerNorm operands");
+        return launch_gemm_pair<opv::kEpiResidualLn>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
     }
   } else if (bn == 256) {
     switch (epi) {
@@ -337,6 +348,7 @@ int gemm_bf16(int epi, bool pair, const CUtensorMap& tm_a, const CUtensorMap& tm
       case opv::kEpiResidual: return launch_gemm_tc<128, opv::kEpiResidual>(tm_a, tm_b, tm_c, ep, M, N, K, stream);
     }
   }
+  if (epi == opv::kEpiResidualLn) return fail(OPV_ERR_UNSUPPORTED, "RESIDUAL_LN epilogue: CTA-pair kernel only (N %% 256 == 0)");
   return fail(OPV_ERR_INVALID_ARGUMENT, "unknown epilogue %d", epi);
 }
 
@@ -513,6 +525,8 @@ int set_option_in(Options& o, const char* name, int64_t value) {
     o.attention_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));
   } else if (strcmp(name, "gemm_group_rows") == 0) {
     o.gemm_group_rows = value != 0;
+  } else if (strcmp(name, "ln_fuse") == 0) {
+    o.ln_fuse = value != 0;
   } else if (strcmp(name, "pdl") == 0) {
     o.pdl = value != 0;
   } else if (strcmp(name, "pdl_late") == 0) {
@@ -814,10 +828,14 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
                                        static_cast<bf16*>(x), T, H, c.vocab_size, c.norm_eps, stream);
     }
     if (rc) return rc;
+    // LayerNorm in the residual GEMMs' epilogue: CTA-pair kernel (H % 256 == 0) and enough 256-row blocks that
+    // giving every CTA pair whole row blocks leaves no pair idle
+    const bool ln_fused = t_opt.ln_fuse && e->gemm_pair && H % 256 == 0 && H <= 1024 &&
+                          (T + 255) / 256 >= static_cast<int64_t>(g_num_sms / 2);
     for (int l = 0; l < L; ++l) {
       const opv_layer_weights& lw = e->layers[l];
       const bool global = c.layer_is_global[l] != 0;
-      if (l > 0) {
+      if (l > 0 && !ln_fused) {
         LaunchScope sc(e, stream, OPV_PROF_LAYERNORM);
         rc = launch_layernorm<bf16>(h, lw.d_attn_norm, static_cast<bf16*>(x), T, H, c.norm_eps, stream);
       }
@@ -843,12 +861,16 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       }
       if (rc) return rc;
       opv::GemmEpilogueArgs er{};
+      opv::GemmEpilogueArgs eln{};  // RESIDUAL_LN: the LayerNorm that follows the projection runs in its epilogue
+      eln.ln_r = h, eln.ln_x = static_cast<bf16*>(x), eln.ln_eps = c.norm_eps;
       {
         LaunchScope sc(e, stream, OPV_PROF_GEMM_WO);
-        rc = gemm_bf16(opv::kEpiResidual, e->gemm_pair, tm_attn, e->tm_wo[l], tm_h, er, T, H, H, stream);
+        eln.ln_w = lw.d_mlp_norm;
+        rc = ln_fused ? gemm_bf16(opv::kEpiResidualLn, true, tm_attn, e->tm_wo[l], tm_h, eln, T, H, H, stream)
+                      : gemm_bf16(opv::kEpiResidual, e->gemm_pair, tm_attn, e->tm_wo[l], tm_h, er, T, H, H, stream);
       }
       if (rc) return rc;
-      {
+      if (!ln_fused) {
         LaunchScope sc(e, stream, OPV_PROF_LAYERNORM);
         rc = launch_layernorm<bf16>(h, lw.d_mlp_norm, static_cast<bf16*>(x), T, H, c.norm_eps, stream);
       }
@@ -871,7 +893,12 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       if (rc) return rc;
       {
         LaunchScope sc(e, stream, OPV_PROF_GEMM_WO2);
-        rc = gemm_bf16(opv::kEpiResidual, e->gemm_pair, tm_act, e->tm_wo2[l], tm_h, er, T, H, I, stream);
+        if (ln_fused && l + 1 < L) {  // the next layer's attn_norm; the final norm stays with the prune head kernel
+          eln.ln_w = e->layers[l + 1].d_attn_norm;
+          rc = gemm_bf16(opv::kEpiResidualLn, true, tm_act, e->tm_wo2[l], tm_h, eln, T, H, I, stream);
+        } else {
+          rc = gemm_bf16(opv::kEpiResidual, e->gemm_pair, tm_act, e->tm_wo2[l], tm_h, er, T, H, I, stream);
+        }
       }
       if (rc) return rc;
     }

@@ -17,9 +17,12 @@
 //   RESIDUAL  R(fp32) += acc, performed in L2 by cp.reduce.async.bulk.tensor .add.f32  (HF:340-341)
 //   GEGLU     C[:, j] = gelu_erf(acc[:, in_j]) * acc[:, gate_j]  (HF:90-91), W rows interleaved per 128;
 //             gelu through the branch-free exp2 form of the Gaussian CDF (common.cuh: gelu_fast)
+//   RESIDUAL_LN  (CTA-pair kernel) RESIDUAL, then the NEXT LayerNorm (HF:318-341: mlp_norm after Wo, the following
+//             layer's attn_norm after Wo2) of the finished rows while they are still in L2: x = LN(R) * w as bf16
 #pragma once
 
 #include "common.cuh"
+#include "pointwise.cuh"
 
 namespace opv {
 
@@ -28,12 +31,15 @@ constexpr int kGemmBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kGemmChunkBytes = 128 * 128;  // staging chunk: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
 
-enum : int { kEpiStore = 0, kEpiRope = 1, kEpiResidual = 2, kEpiGeglu = 3 };
+enum : int { kEpiStore = 0, kEpiRope = 1, kEpiResidual = 2, kEpiGeglu = 3, kEpiResidualLn = 4 };
 
 // Two epilogue groups (8 warps) for every epilogue: the r1b profile showed the K = 512 GEMMs waiting on a
 // single 4-warp epilogue (tensor pipe 64 % active on Wqkv+RoPE); the groups take alternate 128 B chunks.
 __host__ __device__ constexpr int gemm_epi_groups(int /*epi*/) { return 2; }
-__host__ __device__ constexpr int gemm_threads(int epi) { return 64 + 128 * gemm_epi_groups(epi); }
+constexpr int kLnWarps = 4;  // RESIDUAL_LN: warps 10..13 run the LayerNorm of finished row blocks beside the epilogue
+__host__ __device__ constexpr int gemm_threads(int epi) {
+  return 64 + 128 * gemm_epi_groups(epi) + (epi == 4 /* kEpiResidualLn */ ? 32 * kLnWarps : 0);
+}
 
 struct GemmEpilogueArgs {
   const int32_t* pos;  // ROPE: [M] position of each row inside its sequence
@@ -45,6 +51,11 @@ struct GemmEpilogueArgs {
   // (set by the host when there are at least as many row blocks as clusters)
   int32_t group_rows;
   int32_t pdl_late;  // 1 = do not release the dependent kernel early (large forwards, see engine.cu g_pdl_late)
+  // RESIDUAL_LN: after the last column tile of a row block, x[row] = LN(R[row]) * ln_w for the block's rows
+  const float* ln_w;    // [N] LayerNorm weight (no bias: ModernBERT norm_bias = false)
+  const float* ln_r;    // [M, N] fp32, the tensor behind tm_c (the residual stream)
+  __nv_bfloat16* ln_x;  // [M, N] bf16
+  float ln_eps;
 };
 
 // ROPE epilogue: the cos|sin rows (2 x 128 B) of the tile's 128 tokens are staged in shared memory by
@@ -73,6 +84,22 @@ __device__ __forceinline__ void staging_write_row(uint8_t* buf, int r, const uin
         make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
 }
 
+
+// RESIDUAL_LN hand-off from the epilogue-group leaders to the LayerNorm warps: `ready[s]` (2 arrivals, one per group
+// leader) says every reduce-add into this CTA's row block number `blocks` is complete in L2; `done[s]` (kLnWarps
+// arrivals) gives the slot back.  The leaders do not stall for the completion: they signal two chunks into the NEXT
+// tile (cp.async.bulk.wait_group 2 then covers exactly the finished row block) or at the end of the kernel.
+struct LnHandoff {
+  uint64_t* ready;
+  uint64_t* done;
+  int blocks = 0;        // row blocks this CTA has finished issuing
+  bool pending = false;  // the last finished row block has not been signalled yet
+  __device__ __forceinline__ void signal() {  // group leader only
+    const int s = blocks & 1;
+    mbar_wait(&done[s], ((blocks >> 1) & 1) ^ 1);
+    mbar_arrive(&ready[s]);
+  }
+};
 
 // Epilogue-group state: which staging buffer is next and how many buffers the group owns.
 template <int NBUF>
@@ -123,7 +150,8 @@ __device__ __forceinline__ void rope_stage_rows(const GemmEpilogueArgs& ep, uint
 template <int BLOCK_N, int EPI, int NBUF>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogueArgs& ep, const CUtensorMap* tm_c,
                                                    StagingRing<NBUF>& ring, const uint8_t* rope_cs, uint32_t taddr,
-                                                   int r_tile, int64_t row, int M, int m_blk, int n_blk, int group) {
+                                                   int r_tile, int64_t row, int M, int m_blk, int n_blk, int group,
+                                                   LnHandoff* ln = nullptr) {
   const int row0 = m_blk * kGemmBlockM;
   if constexpr (EPI == kEpiStore) {
 #pragma unroll 1
@@ -169,7 +197,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogueArgs& ep, c
       const int col0 = n_blk * BLOCK_N + hd * 64;
       ring.release(buf, [&](uint8_t* b) { tma_store_2d(tm_c, b, col0, row0); });
     }
-  } else if constexpr (EPI == kEpiResidual) {
+  } else if constexpr (EPI == kEpiResidual || EPI == kEpiResidualLn) {
 #pragma unroll 1
     for (int c = group; c < BLOCK_N / 32; c += gemm_epi_groups(EPI)) {  // 32 fp32 columns = 128 B per row
       uint32_t w[32];
@@ -178,6 +206,16 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogueArgs& ep, c
       staging_write_row(buf, r_tile, w);
       const int col0 = n_blk * BLOCK_N + c * 32;
       ring.release(buf, [&](uint8_t* b) { tma_reduce_add_2d(tm_c, b, col0, row0); });
+      if constexpr (EPI == kEpiResidualLn) {
+        if (c == group + gemm_epi_groups(EPI) && ln->pending) {  // second chunk of this tile issued
+          if (ring.leader) {
+            tma_store_wait_complete<2>();  // all but this tile's two bulk groups: the previous row block is final in L2
+            ln->signal();
+          }
+          ln->pending = false;
+          ++ln->blocks;
+        }
+      }
     }
   } else {  // kEpiGeglu: tile columns [0,128) = "input", [128,256) = "gate" of the same 128 features
     static_assert(EPI != kEpiGeglu || BLOCK_N == 256, "GeGLU epilogue needs BLOCK_N = 256");
@@ -198,6 +236,53 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpilogueArgs& ep, c
     ring.release(buf, [&](uint8_t* b) { tma_store_2d(tm_c, b, col0, row0); });
   }
 }
+
+// RESIDUAL_LN: LayerNorm of the 128 rows [row0, row0 + 128) of R by the kLnWarps LayerNorm warps, one warp per row
+// and four (N <= 512) or two rows in flight per warp (ld.global.cg: never a stale L1 line).  Same statistics code as
+// layernorm_kernel (pointwise.cuh), hence bit-identical x.
+// MEASURED (B200, base-130M, 131 072 tokens): correct, but NOT a win, so `ln_fuse` is off by
+// default.  The idea was that the rows are re-read from L2 right after this CTA's own reduce-adds completed them.
+// They are not there any more: with all 148 CTAs streaming, ~113 MB pass through the 126 MB L2 per round of row
+// blocks (~16 us), so the re-reads go to DRAM (Wo: 404 -> 653-669 MB read per launch, also with an evict_last
+// policy on the reduce-adds and with the LayerNorm signalled at once), and giving a CTA pair whole row blocks
+// separates the two column tiles' reads of the same A rows in time (Wo2: 807 -> 1396-1468 MB).  Wo 2.52 -> 4.5,
+// Wo2 4.25 -> 6.2 ms per step against 2.45 ms of standalone LayerNorm launches saved.
+template <int VEC>
+__device__ __forceinline__ void epilogue_ln_rows(const GemmEpilogueArgs& ep, int row0, int M, int lw, int lane) {
+  constexpr int N = VEC * 128;
+  constexpr int R = VEC <= 4 ? 4 : 2;  // rows in flight per warp (register budget: R * VEC float4)  // rows in flight per warp (register budget: R * VEC float4)
+  float4 g[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) g[i] = __ldg(reinterpret_cast<const float4*>(ep.ln_w + (i * 32 + lane) * 4));
+#pragma unroll 1
+  for (int rb = lw; rb < kGemmBlockM; rb += kLnWarps * R) {
+    float4 v[R][VEC];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int64_t row = min(static_cast<int64_t>(row0) + rb + kLnWarps * j, static_cast<int64_t>(M) - 1);  // clamped: loads are unconditional
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[j][i] = __ldcg(reinterpret_cast<const float4*>(ep.ln_r + row * N + (i * 32 + lane) * 4));
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int64_t row = static_cast<int64_t>(row0) + rb + kLnWarps * j;
+      if (row < M) {
+        float mean, rstd;
+        row_norm_stats<VEC>(v[j], ep.ln_eps, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          float4 o;
+          o.x = (v[j][i].x - mean) * rstd * g[i].x;
+          o.y = (v[j][i].y - mean) * rstd * g[i].y;
+          o.z = (v[j][i].z - mean) * rstd * g[i].z;
+          o.w = (v[j][i].w - mean) * rstd * g[i].w;
+          store4(ep.ln_x + row * N + (i * 32 + lane) * 4, o);
+        }
+      }
+    }
+  }
+}
+
 
 // tm_c: STORE/ROPE/GEGLU bf16 [M, ldc] with a 64-column x 128-row box; RESIDUAL fp32 [M, N] with a
 // 32-column x 128-row box (both SWIZZLE_128B).  TMA clips rows >= M.
@@ -401,6 +486,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
   uint64_t* tmem_full = empty_bar + L::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* ln_ready = tmem_empty + 4;  // RESIDUAL_LN: [2] row block final in L2 (one arrival per epilogue-group leader)
+  uint64_t* ln_done = ln_ready + 2;     //              [2] row block normalised (one arrival per LayerNorm warp)
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -425,6 +512,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);                  // multicast tcgen05.commit from the leader
       mbar_init(&tmem_empty[s], 2 * 4 * kGroups);   // epilogue warps of BOTH CTAs (used on the leader only)
+      mbar_init(&ln_ready[s], kGroups);
+      mbar_init(&ln_done[s], kLnWarps);
     }
     fence_mbar_init();
   }
@@ -493,7 +582,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else {
+  } else if (warp < 2 + 4 * kGroups) {
     // ------------------------------ epilogue warps (both CTAs) ----------------
     const int quarter = warp & 3;
     const int group = (warp - 2) >> 2;
@@ -502,6 +591,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
     ring.base = staging + group * kBufsPerGroup * kGemmChunkBytes;
     ring.bar_id = 1 + group;
     ring.leader = ((warp - 2) & 3) == 0 && lane == 0;
+    LnHandoff ln;
+    ln.ready = ln_ready, ln.done = ln_done;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = 0;; ++u) {
@@ -519,14 +610,45 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __
       tc_fence_after();
       const int64_t row = static_cast<int64_t>(m_blk) * kGemmBlockM + r_tile;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-      gemm_epilogue_tile<BLOCK_N, EPI>(ep, &tm_c, ring, rope_cs, taddr, r_tile, row, M, m_blk, n_blk, group);
+      gemm_epilogue_tile<BLOCK_N, EPI>(ep, &tm_c, ring, rope_cs, taddr, r_tile, row, M, m_blk, n_blk, group, &ln);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_pair_leader(&tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      // group_rows order: the last column tile ends this CTA's 128-row block; its LayerNorm is handed over two chunks
+      // into the next tile (gemm_epilogue_tile) or below
+      if constexpr (EPI == kEpiResidualLn) ln.pending = n_blk == num_n - 1;
     }
-    if (ring.leader) tma_store_wait_all();
+    if (ring.leader) {
+      tma_store_wait_all();
+      if constexpr (EPI == kEpiResidualLn) {
+        if (ln.pending) ln.signal();
+      }
+    }
+  } else {
+    // ------------------------------ LayerNorm warps (RESIDUAL_LN, both CTAs) --
+    if constexpr (EPI == kEpiResidualLn) {
+      const int lw = warp - (2 + 4 * kGroups);
+      int blocks = 0;
+      for (int u = 0;; ++u) {
+        int m_pair, n_blk;
+        if (!pair_tile(u, first_tile, tile_step, num_tiles, num_pairs_m, num_n, ep.group_rows, m_pair, n_blk)) break;
+        if (n_blk != num_n - 1) continue;
+        const int row0 = (m_pair * 2 + cta_rank) * kGemmBlockM;
+        const int s = blocks & 1;
+        mbar_wait(&ln_ready[s], (blocks >> 1) & 1);
+        switch (N >> 7) {
+          case 2: epilogue_ln_rows<2>(ep, row0, M, lw, lane); break;
+          case 4: epilogue_ln_rows<4>(ep, row0, M, lw, lane); break;
+          case 6: epilogue_ln_rows<6>(ep, row0, M, lw, lane); break;
+          default: epilogue_ln_rows<8>(ep, row0, M, lw, lane); break;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ln_done[s]);
+        ++blocks;
+      }
+    }
   }
 
   tc_fence_before();

@@ -155,6 +155,29 @@ def test_programmatic_dependent_launch_is_bit_identical(name):
         assert np.array_equal(prune, outs[0][0]) and np.array_equal(rank, outs[0][1])
 
 
+@pytest.mark.parametrize("name", FAMILIES)
+def test_layernorm_in_the_residual_gemm_epilogue_is_bit_identical(name):
+    """``ln_fuse`` (off by default: measured slower): forwards with at least one 256-row block per
+    CTA pair run mlp_norm / the next layer's attn_norm inside the Wo / Wo2 GEMM (RESIDUAL_LN, H = 256 / 512 / 768 /
+    1024) with the statistics code of ``layernorm_kernel``: the same bits as the standalone launches, including the
+    ragged last row block."""
+    from open_provence_b200 import ops
+
+    cfg, sd, _ = _case(name, layers=3)
+    rng = np.random.default_rng(23)
+    lengths = [2048] * 9 + [777, 1, 300, 129]  # 19 639 tokens: 77 row pairs, the last one 183 rows
+    seqs = [rng.integers(3, cfg["vocab_size"], size=n).tolist() for n in lengths]
+    outs = []
+    for fuse in (1, 0):
+        ops.set_option("ln_fuse", fuse)
+        try:
+            outs.append(_run(cfg, sd, seqs, "bf16"))
+        finally:
+            ops.set_option("ln_fuse", 0)
+    assert np.isfinite(outs[0][0]).all() and np.isfinite(outs[0][1]).all()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("name", ["xsmall-30M", "en-gte-149M"])
 def test_family_mean_pooling_fp32(name):
     """classifier_pooling = "mean" at H = 256 / 768 against the fp64 oracle."""
