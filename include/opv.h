@@ -138,8 +138,10 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
  * error 7.5e-5, far below the bf16 rounding of the probabilities).  "attention_trace_ptr": device buffer for the clock64() timeline of
  * tools/attn_check.py (0 = off, the product setting).  "gemm_pair": 1 = CTA-pair (cta_group::2) GEMM for 256-wide
  * tiles (default), 0 = single-CTA kernel.  "gemm_group_rows": row-grouped tile order of the RoPE GEMM (default 1).
- * "ln_fuse": 1 = large bf16 forwards run each LayerNorm inside the residual GEMM that completes its rows (bit-identical
- * results; measured slower on B200 because the re-reads miss L2, so default 0 = standalone LayerNorm launches).
+ * "ln_fuse": 0 = standalone LayerNorm launches; 1 = large bf16 forwards run each LayerNorm inside the residual GEMM that
+ * completes its rows, re-reading them (bit-identical results; measured slower on B200: the re-reads miss L2); 2 = full-row
+ * residual GEMM with the LayerNorm computed from TMEM (default; hidden size 256 / 512: attn.Wo, and mlp.Wo for 256), for
+ * forwards of at least "ln_fuse_min_blocks" 256-row blocks (-1 = measured crossover: 0 for hidden size 256, 48 for 512).
  * "pdl": 1 = GEMM / attention / LayerNorm kernels are launched with programmatic stream serialization so that each
  * kernel's prologue overlaps its predecessor's tail (default), 0 = plain stream order; "pdl_max_tokens": forwards
  * with more packed tokens than this do not release their dependents early (default 32768, profiles/r1t_pdl.md);
@@ -272,6 +274,12 @@ typedef enum opv_epilogue {
 int opv_op_gemm(int32_t dtype, int32_t epilogue, const void* d_a, const void* d_w, void* d_c, int64_t m, int32_t n,
                 int32_t k, const int32_t* d_pos, const float* d_cos, const float* d_sin, int32_t hidden_size,
                 void* stream);
+/* Residual GEMM with the following LayerNorm from on-chip data (bf16 A / W, CTA-pair tcgen05 kernel, N in {256, 512}):
+ * R += A[M,K] . W[N,K]^T (fp32 [M, N], in place), X = LN(R) * ln_w (bf16 [M, N]).  Replaces the reference's
+ * hidden_states = hidden_states + attn / mlp output followed by mlp_norm / the next layer's attn_norm (transformers
+ * modeling_modernbert.py:318-341) for attn.Wo (and mlp.Wo when N = 256); engine option "ln_fuse" = 2. */
+int opv_op_gemm_residual_ln(const void* d_a, const void* d_w, float* d_r, void* d_x, const float* d_ln_w, float eps,
+                            int64_t m, int32_t n, int32_t k, void* stream);
 /* x = LN(h) * w ; out operand dtype. h fp32 [M, H]. */
 int opv_op_layernorm(int32_t dtype, const float* d_h, const float* d_w, void* d_out, int64_t m, int32_t hidden,
                      float eps, void* stream);

@@ -21,6 +21,7 @@
 #include "attention_tcgen05_v3.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_rowln.cuh"
 #include "gemm_tcgen05.cuh"
 #include "pointwise.cuh"
 
@@ -119,11 +120,20 @@ struct Options {
   int gemm_pair = 1;
   // ROPE GEMM: 1 = a cluster finishes all column tiles of a row block before the next row block (cos|sin staged once)
   int gemm_group_rows = 1;
-  // 1 = bf16 forwards with at least one 256-row block per CTA pair run every LayerNorm but the first and the last inside
-  // the residual GEMM that completes its input rows (RESIDUAL_LN, gemm_tcgen05.cuh: four extra warps normalise a row
-  // block once its reduce-adds are complete); 0 = standalone layernorm_kernel launches (default).  Bit-identical
-  // results; measured 2122-2204 against 2221-2260 pairs/s (the re-reads miss L2, see gemm_tcgen05.cuh), so off.
-  int ln_fuse = 0;
+  // Where the LayerNorms between the projections run (bf16 forwards with at least one 256-row block per CTA pair):
+  // 0 = standalone layernorm_kernel launches;
+  // 1 = inside the residual GEMM that completes the rows, RE-READING them (RESIDUAL_LN, gemm_tcgen05.cuh): bit-identical,
+  //     measured slower (2122-2204 against 2221-2260 pairs/s: the re-reads miss L2);
+  // 2 = (default) full-row residual GEMM with the LayerNorm computed from TMEM (gemm_rowln.cuh) for attn.Wo when the
+  //     hidden size is 256 or 512, and for mlp.Wo when it is 256: base-130M 28.42 -> 28.0-28.3 ms per step, xsmall-30M
+  //     4.97 -> 4.66 ms; other widths keep the standalone launches.
+  int ln_fuse = 2;
+  // ln_fuse = 2 applies to forwards with at least this many 256-row blocks; -1 = measured crossover (B200,
+  // tools/lnfuse_sweep.sh): hidden size 256 always (2048 .. 65536 tokens: 3-5 % faster at every size), 512 from 48
+  // blocks (2048 / 4096 / 8192 tokens: 7.5 / 6 / 3.4 % slower -- half as many CTA pairs busy as with 256-wide tiles
+  // -- 16384 tokens and up: 0.3-1.4 % faster).  Below the crossover the LayerNorm statistics are summed in
+  // layernorm_kernel's order, above in gemm_rowln's: x can differ by one bf16 ulp in a few elements per 10^5.
+  int ln_fuse_min_blocks = -1;
   // 1 = the kernels that call pdl_wait() (GEMMs, attention, LayerNorm family) are launched with programmatic stream
   // serialization, so each one's prologue overlaps its predecessor's tail; 0 = plain stream order
   int pdl = 1;
@@ -212,6 +222,8 @@ int ensure_device_setup() {
     if (int rc = set_gemm_pair_attr<opv::kEpiResidual>()) return rc;
     if (int rc = set_gemm_pair_attr<opv::kEpiGeglu>()) return rc;
     if (int rc = set_gemm_pair_attr<opv::kEpiResidualLn>()) return rc;
+    OPV_CUDA(cudaFuncSetAttribute(opv::gemm_rowln_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  opv::RowLnSmemLayout::kTotal));
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   opv::FaSmemLayout<true>::kTotal));
     OPV_CUDA(cudaFuncSetAttribute(opv::attention_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -303,6 +315,22 @@ int launch_gemm_pair(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUt
   launch_pdl(opv::gemm_bf16_tcgen05_pair_kernel<EPI>, dim3(2 * clusters), dim3(opv::gemm_threads(EPI)),
              opv::GemmPairSmemLayout<EPI>::kTotal, stream, tm_a, tm_b, tm_c, ep_launch, (int)M, N, K);
   OPV_LAUNCH_CHECK("gemm_bf16_tcgen05_pair_kernel");
+  return OPV_OK;
+}
+
+// Residual GEMM + the following LayerNorm from on-chip data (gemm_rowln.cuh): N = hidden size in {256, 512}.
+int launch_gemm_rowln(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_r, const CUtensorMap& tm_x,
+                      const float* ln_w, float eps, int64_t M, int N, int K, cudaStream_t stream) {
+  if (M <= 0) return OPV_OK;
+  if ((N != 256 && N != 512) || K % opv::kGemmBlockK != 0)
+    return fail(OPV_ERR_UNSUPPORTED, "row-LN GEMM needs N in {256, 512} and K %% 64 == 0 (N = %d, K = %d)", N, K);
+  if (M > 0x7fffff00LL) return fail(OPV_ERR_UNSUPPORTED, "M = %lld rows exceeds the int32 tile range", (long long)M);
+  const int64_t pairs_m = (M + 2 * opv::kGemmBlockM - 1) / (2 * opv::kGemmBlockM);
+  const int max_clusters = g_num_sms / 2;
+  const int clusters = static_cast<int>(pairs_m < max_clusters ? pairs_m : max_clusters);
+  launch_pdl(opv::gemm_rowln_pair_kernel, dim3(2 * clusters), dim3(320), opv::RowLnSmemLayout::kTotal, stream, tm_a, tm_b,
+             tm_r, tm_x, ln_w, eps, pdl_late_flag(), (int)M, N, K);
+  OPV_LAUNCH_CHECK("gemm_rowln_pair_kernel");
   return OPV_OK;
 }
 
@@ -526,7 +554,10 @@ int set_option_in(Options& o, const char* name, int64_t value) {
   } else if (strcmp(name, "gemm_group_rows") == 0) {
     o.gemm_group_rows = value != 0;
   } else if (strcmp(name, "ln_fuse") == 0) {
-    o.ln_fuse = value != 0;
+    if (value < 0 || value > 2) return fail(OPV_ERR_INVALID_ARGUMENT, "ln_fuse must be 0, 1 or 2");
+    o.ln_fuse = static_cast<int>(value);
+  } else if (strcmp(name, "ln_fuse_min_blocks") == 0) {
+    o.ln_fuse_min_blocks = static_cast<int>(value);
   } else if (strcmp(name, "pdl") == 0) {
     o.pdl = value != 0;
   } else if (strcmp(name, "pdl_late") == 0) {
@@ -830,12 +861,17 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
     if (rc) return rc;
     // LayerNorm in the residual GEMMs' epilogue: CTA-pair kernel (H % 256 == 0) and enough 256-row blocks that
     // giving every CTA pair whole row blocks leaves no pair idle
-    const bool ln_fused = t_opt.ln_fuse && e->gemm_pair && H % 256 == 0 && H <= 1024 &&
-                          (T + 255) / 256 >= static_cast<int64_t>(g_num_sms / 2);
+    const bool ln_rows_ok = e->gemm_pair && (T + 255) / 256 >= static_cast<int64_t>(g_num_sms / 2);
+    const bool ln_fused = t_opt.ln_fuse == 1 && ln_rows_ok && H % 256 == 0 && H <= 1024;
+    // ln_fuse = 2: full-row residual GEMM with the LayerNorm from TMEM (gemm_rowln.cuh).  attn.Wo for H = 256 / 512;
+    // mlp.Wo only for H = 256, where the second accumulator keeps the MMAs running during the LayerNorm passes.
+    const int64_t ln_min_blocks = t_opt.ln_fuse_min_blocks < 0 ? (H == 256 ? 0 : 48) : t_opt.ln_fuse_min_blocks;
+    const bool ln_row_wo = t_opt.ln_fuse == 2 && e->gemm_pair && (T + 255) / 256 >= ln_min_blocks && (H == 256 || H == 512);
+    const bool ln_row_wo2 = ln_row_wo && H == 256;
     for (int l = 0; l < L; ++l) {
       const opv_layer_weights& lw = e->layers[l];
       const bool global = c.layer_is_global[l] != 0;
-      if (l > 0 && !ln_fused) {
+      if (l > 0 && !ln_fused && !ln_row_wo2) {
         LaunchScope sc(e, stream, OPV_PROF_LAYERNORM);
         rc = launch_layernorm<bf16>(h, lw.d_attn_norm, static_cast<bf16*>(x), T, H, c.norm_eps, stream);
       }
@@ -866,11 +902,14 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       {
         LaunchScope sc(e, stream, OPV_PROF_GEMM_WO);
         eln.ln_w = lw.d_mlp_norm;
-        rc = ln_fused ? gemm_bf16(opv::kEpiResidualLn, true, tm_attn, e->tm_wo[l], tm_h, eln, T, H, H, stream)
-                      : gemm_bf16(opv::kEpiResidual, e->gemm_pair, tm_attn, e->tm_wo[l], tm_h, er, T, H, H, stream);
+        if (ln_row_wo)
+          rc = launch_gemm_rowln(tm_attn, e->tm_wo[l], tm_h, tm_x, lw.d_mlp_norm, c.norm_eps, T, H, H, stream);
+        else
+          rc = ln_fused ? gemm_bf16(opv::kEpiResidualLn, true, tm_attn, e->tm_wo[l], tm_h, eln, T, H, H, stream)
+                        : gemm_bf16(opv::kEpiResidual, e->gemm_pair, tm_attn, e->tm_wo[l], tm_h, er, T, H, H, stream);
       }
       if (rc) return rc;
-      if (!ln_fused) {
+      if (!ln_fused && !ln_row_wo) {
         LaunchScope sc(e, stream, OPV_PROF_LAYERNORM);
         rc = launch_layernorm<bf16>(h, lw.d_mlp_norm, static_cast<bf16*>(x), T, H, c.norm_eps, stream);
       }
@@ -893,7 +932,9 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       if (rc) return rc;
       {
         LaunchScope sc(e, stream, OPV_PROF_GEMM_WO2);
-        if (ln_fused && l + 1 < L) {  // the next layer's attn_norm; the final norm stays with the prune head kernel
+        if (ln_row_wo2 && l + 1 < L) {
+          rc = launch_gemm_rowln(tm_act, e->tm_wo2[l], tm_h, tm_x, e->layers[l + 1].d_attn_norm, c.norm_eps, T, H, I, stream);
+        } else if (ln_fused && l + 1 < L) {  // the next layer's attn_norm; the final norm stays with the prune head kernel
           eln.ln_w = e->layers[l + 1].d_attn_norm;
           rc = gemm_bf16(opv::kEpiResidualLn, true, tm_act, e->tm_wo2[l], tm_h, eln, T, H, I, stream);
         } else {
@@ -1121,6 +1162,20 @@ int opv_op_gemm(int32_t dtype, int32_t epilogue, const void* d_a, const void* d_
   if (epilogue == OPV_EPI_ROPE && (!d_pos || !d_cos || !d_sin || n != 3 * hidden_size))
     return fail(OPV_ERR_INVALID_ARGUMENT, "ROPE epilogue needs pos/cos/sin and N == 3 * hidden_size");
   return gemm_bf16(epilogue, pair, tm_a, tm_b, tm_c, ep, m, n, k, stream);
+}
+
+int opv_op_gemm_residual_ln(const void* d_a, const void* d_w, float* d_r, void* d_x, const float* d_ln_w, float eps,
+                            int64_t m, int32_t n, int32_t k, void* stream_) {
+  if (!d_a || !d_w || !d_r || !d_x || !d_ln_w) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_op_gemm_residual_ln: null buffer");
+  if (int rc = ensure_device_setup()) return rc;
+  t_opt = defaults_snapshot();
+  if (m <= 0) return OPV_OK;
+  CUtensorMap tm_a, tm_b, tm_r, tm_x;
+  if (int rc = make_tmap_bf16(&tm_a, d_a, m, k, opv::kGemmBlockM)) return rc;
+  if (int rc = make_tmap_bf16(&tm_b, d_w, n, k, 128)) return rc;  // half of the 256-row W tile per CTA
+  if (int rc = make_tmap_2d(&tm_r, d_r, true, m, n, opv::kGemmBlockM)) return rc;
+  if (int rc = make_tmap_bf16(&tm_x, d_x, m, n, opv::kGemmBlockM)) return rc;
+  return launch_gemm_rowln(tm_a, tm_b, tm_r, tm_x, d_ln_w, eps, m, n, k, static_cast<cudaStream_t>(stream_));
 }
 
 int opv_op_layernorm(int32_t dtype, const float* d_h, const float* d_w, void* d_out, int64_t m, int32_t hidden,

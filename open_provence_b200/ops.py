@@ -56,6 +56,22 @@ def gemm(
     return out
 
 
+def gemm_residual_ln(a: torch.Tensor, w: torch.Tensor, r: torch.Tensor, ln_weight: torch.Tensor, eps: float) -> torch.Tensor:
+    """``r += a @ w.T`` in place (fp32) and returns ``LayerNorm(r) * ln_weight`` as bf16, from one kernel
+    (``opv_op_gemm_residual_ln``; hidden size 256 or 512)."""
+    lib = N.load()
+    assert a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
+    m, k = a.shape
+    n = w.shape[0]
+    assert r.dtype == torch.float32 and r.shape == (m, n) and r.is_contiguous()
+    x = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = lib.opv_op_gemm_residual_ln(a.data_ptr(), w.data_ptr(), r.data_ptr(), x.data_ptr(), ln_weight.data_ptr(),
+                                         float(eps), m, n, k, _stream(a))
+    N.check(rc, "opv_op_gemm_residual_ln")
+    return x
+
+
 def layernorm(h: torch.Tensor, weight: torch.Tensor, eps: float, out_dtype: torch.dtype) -> torch.Tensor:
     lib = N.load()
     m, hidden = h.shape

@@ -157,7 +157,7 @@ def test_programmatic_dependent_launch_is_bit_identical(name):
 
 @pytest.mark.parametrize("name", FAMILIES)
 def test_layernorm_in_the_residual_gemm_epilogue_is_bit_identical(name):
-    """``ln_fuse`` (off by default: measured slower): forwards with at least one 256-row block per
+    """``ln_fuse=1`` (not the default: measured slower): forwards with at least one 256-row block per
     CTA pair run mlp_norm / the next layer's attn_norm inside the Wo / Wo2 GEMM (RESIDUAL_LN, H = 256 / 512 / 768 /
     1024) with the statistics code of ``layernorm_kernel``: the same bits as the standalone launches, including the
     ragged last row block."""
@@ -173,9 +173,35 @@ def test_layernorm_in_the_residual_gemm_epilogue_is_bit_identical(name):
         try:
             outs.append(_run(cfg, sd, seqs, "bf16"))
         finally:
-            ops.set_option("ln_fuse", 0)
+            ops.set_option("ln_fuse", 2)
     assert np.isfinite(outs[0][0]).all() and np.isfinite(outs[0][1]).all()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("name", ["xsmall-30M", "base-130M"])
+def test_layernorm_from_tmem_in_the_residual_gemm(name):
+    """``ln_fuse=2`` (default): attn.Wo (and mlp.Wo at H = 256) run on the full-row kernel that computes the following LayerNorm
+    from TMEM (gemm_rowln.cuh).  Same fp32 residual arithmetic, two-pass statistics with a different summation order:
+    the forward stays within bf16 rounding noise of the standalone-LayerNorm forward and of the fp64 oracle bounds."""
+    from open_provence_b200 import ops
+
+    cfg, sd, _ = _case(name, layers=3)
+    rng = np.random.default_rng(23)
+    lengths = [2048] * 9 + [777, 1, 300, 129]
+    seqs = [rng.integers(3, cfg["vocab_size"], size=n).tolist() for n in lengths]
+    outs = []
+    for fuse in (2, 0):
+        ops.set_option("ln_fuse", fuse)
+        try:
+            outs.append(_run(cfg, sd, seqs, "bf16"))
+        finally:
+            ops.set_option("ln_fuse", 2)
+    (p2, r2), (p0, r0) = outs
+    assert np.isfinite(p2).all() and np.isfinite(r2).all()
+    scale = max(1.0, np.abs(p0).max())
+    d_prune, d_rank = np.abs(p2 - p0).max(), np.abs(r2 - r0).max()
+    print(f"{name}: ln_fuse=2 vs 0: prune {d_prune:.2e} (scale {scale:.1f}) rank {d_rank:.2e}")
+    assert d_prune < 4e-3 * scale and d_rank < 4e-3
 
 
 @pytest.mark.parametrize("name", ["xsmall-30M", "en-gte-149M"])

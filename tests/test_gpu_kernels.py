@@ -74,6 +74,31 @@ def test_gemm_bf16_residual(m, n, k, gemm_kernel):
     assert err < 1e-4 * max(1.0, ref.abs().max().item()), f"residual epilogue max err {err:.3e}"
 
 
+@pytest.mark.parametrize("m,n,k", [(300, 256, 256), (1000, 512, 512), (4113, 256, 1024), (40001, 512, 512),
+                                   (76033, 256, 256), (1, 512, 64)])
+def test_gemm_residual_layernorm_rows(m, n, k):
+    """Full-row residual GEMM with the following LayerNorm from TMEM (``opv_op_gemm_residual_ln``, gemm_rowln.cuh):
+    the new residual against fp32 torch, X against ``F.layer_norm`` of the residual the kernel itself wrote (so the
+    bound is the bf16 rounding of X, 2^-8 relative), ragged last row block, more row blocks than CTA pairs."""
+    a = _rand_bf16((m, k), 31)
+    w = _rand_bf16((n, k), 32, 0.05)
+    g = torch.Generator().manual_seed(33)
+    r0 = (torch.randn((m, n), generator=g) * 3.0 + torch.randn((m, 1), generator=g)).to(DEV)  # rows with a mean
+    gamma = (1.0 + 0.2 * torch.randn((n,), generator=g)).to(DEV)
+    r = r0.clone()
+    x = ops.gemm_residual_ln(a, w, r, gamma, 1e-5)
+    torch.cuda.synchronize()
+    ref_r = r0 + a.float() @ w.float().T
+    err = (r - ref_r).abs().max().item()
+    assert err < 1e-4 * max(1.0, ref_r.abs().max().item()), f"residual max err {err:.3e}"
+    ref_x = torch.nn.functional.layer_norm(r, (n,), gamma, None, 1e-5)
+    _bf16_close(x, ref_x, f"row LayerNorm {m}x{n}x{k}")
+    # and the statistics themselves, against fp64
+    r64 = r.double()
+    ref64 = ((r64 - r64.mean(1, keepdim=True)) / torch.sqrt(r64.var(1, unbiased=False, keepdim=True) + 1e-5) * gamma.double())
+    assert (x.double() - ref64).abs().max().item() < 2.0**-7 * ref64.abs().max().item()
+
+
 def _rope_ref(qkv: torch.Tensor, pos: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, hidden: int) -> torch.Tensor:
     t = qkv.shape[0]
     heads = hidden // 64
