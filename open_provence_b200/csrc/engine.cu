@@ -328,7 +328,7 @@ int launch_gemm_rowln(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CU
   const int64_t pairs_m = (M + 2 * opv::kGemmBlockM - 1) / (2 * opv::kGemmBlockM);
   const int max_clusters = g_num_sms / 2;
   const int clusters = static_cast<int>(pairs_m < max_clusters ? pairs_m : max_clusters);
-  launch_pdl(opv::gemm_rowln_pair_kernel, dim3(2 * clusters), dim3(320), opv::RowLnSmemLayout::kTotal, stream, tm_a, tm_b,
+  launch_pdl(opv::gemm_rowln_pair_kernel, dim3(2 * clusters), dim3(opv::kRowLnThreads), opv::RowLnSmemLayout::kTotal, stream, tm_a, tm_b,
              tm_r, tm_x, ln_w, eps, pdl_late_flag(), (int)M, N, K);
   OPV_LAUNCH_CHECK("gemm_rowln_pair_kernel");
   return OPV_OK;

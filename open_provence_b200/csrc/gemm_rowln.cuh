@@ -15,7 +15,8 @@
 // HBM bytes per token: A + 4N (old) + 4N (new) + 2N (X) against A + 8N + (4N + 2N) for GEMM + LayerNorm launches.
 //
 // Same producer / MMA-issuer structure as gemm_bf16_tcgen05_pair_kernel (cta_group::2, 256 x 256 tiles, group_rows
-// tile order); 3 operand stages, 4 epilogue buffers of 16 KB per epilogue group (load -> modify in place -> store).
+// tile order); 3 operand stages, 8 epilogue warps in 2 column groups with four 16 KB buffers each (load -> modify in
+// place -> store, three loads ahead).
 #pragma once
 
 #include "gemm_tcgen05.cuh"
@@ -23,15 +24,19 @@
 namespace opv {
 
 constexpr int kRowLnStages = 3;
-constexpr int kRowLnBufs = 4;  // per epilogue group
+constexpr int kRowLnGroups = 2;                  // epilogue groups of 4 warps; group g takes the 32-column chunks c = g (mod groups). Measured with 4 groups (16 warps, 2 buffers each, one load ahead): attn.Wo 3.45 -> 3.92 ms per step -- the depth of the load pipeline matters, not the number of warps
+constexpr int kRowLnBufs = 8 / kRowLnGroups;     // 16 KB buffers per epilogue group (8 in total)
 constexpr int kRowLnLoadAhead = kRowLnBufs - 1;  // old-residual loads in flight per group
+constexpr int kRowLnThreads = 64 + 128 * kRowLnGroups;
+constexpr int kRowLnChunksPerTile = 8 / kRowLnGroups;  // "L" slots per 256-column tile and group
+constexpr int kRowLnXPerTile = 4 / kRowLnGroups;       // "X" slots per tile and group
 
 struct RowLnSmemLayout {
   static constexpr int kStageA = kGemmBlockM * kGemmBlockK * 2;
   static constexpr int kStageB = 128 * kGemmBlockK * 2;
   static constexpr int kTileBytes = kRowLnStages * (kStageA + kStageB);  //  96 KB
-  static constexpr int kBufBytes = 2 * kRowLnBufs * kGemmChunkBytes;     // 128 KB
-  static constexpr int kStatBytes = 2 * 2 * kGemmBlockM * 4;             // [step parity][group][row] fp32 partial sums
+  static constexpr int kBufBytes = kRowLnGroups * kRowLnBufs * kGemmChunkBytes;  // 128 KB
+  static constexpr int kStatBytes = kRowLnGroups * kGemmBlockM * 4;      // [group][row] fp32 partial sums
   static constexpr int kBarrierBytes = 192;
   // no alignment slack: the dynamic segment is the kernel's only shared memory and starts 1024-aligned (checked)
   static constexpr int kTotal = kTileBytes + kBufBytes + kStatBytes + kBarrierBytes;
@@ -55,7 +60,7 @@ __device__ __forceinline__ void staging_read_row(const uint8_t* buf, int r, uint
 }
 
 // tm_r: fp32 [M, N] residual stream, 32-column x 128-row box (loads AND stores); tm_x: bf16 [M, N], 64-column box.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kRowLnThreads, 1)
 gemm_rowln_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                        const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_x,
                        const float* __restrict__ ln_w, const float ln_eps, const int pdl_late, const int M, const int N,
@@ -73,7 +78,7 @@ gemm_rowln_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
   uint64_t* tmem_full = empty_bar + kRowLnStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* ld_full = tmem_empty + 2;  // [group][kRowLnBufs]: old-residual chunk landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_full + 2 * kRowLnBufs);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_full + kRowLnGroups * kRowLnBufs);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -97,9 +102,9 @@ gemm_rowln_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 2 * 4 * 2);  // epilogue warps of both CTAs
+      mbar_init(&tmem_empty[s], 2 * 4 * kRowLnGroups);  // epilogue warps of both CTAs
     }
-    for (int s = 0; s < 2 * kRowLnBufs; ++s) mbar_init(&ld_full[s], 1);
+    for (int s = 0; s < kRowLnGroups * kRowLnBufs; ++s) mbar_init(&ld_full[s], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -121,6 +126,9 @@ gemm_rowln_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       const int row0 = (m_pair * 2 + cta_rank) * kGemmBlockM;
       for (int n_blk = 0; n_blk < tiles_per_row; ++n_blk) {
         const int wrow0 = n_blk * BLOCK_N + cta_rank * 128;
+        // (Measured and not kept: an L2 prefetch of the NEXT row block's A rows from here, to shorten the first tile after
+        // the accumulators come back -- ncu: 31 % of the epilogue warps' time is the wait for that tile.  attn.Wo
+        // 3.45 -> 3.70 ms per step, xsmall mlp.Wo 1.14 -> 1.43: the prefetched lines are evicted before their load.)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
@@ -169,29 +177,33 @@ gemm_rowln_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
     }
   } else {
     // ------------------------------ epilogue warps (both CTAs) ----------------
+    // kRowLnGroups groups of 4 warps (one warp per TMEM lane quarter) split the columns.
     // Per row block and group: n_load "L" slots (one 32-column fp32 chunk each: load old, add, store new) followed
     // by n_x "X" slots (one 64-column bf16 chunk of X each).  Slot u of the group's running count lives in buffer
-    // u % kRowLnBufs; the leader issues the load of slot u + kRowLnLoadAhead right after committing the store of slot u,
-    // when cp.async.bulk.wait_group.read 1 says the previous occupant of that buffer (slot u - 1) has been read.
+    // u % kRowLnBufs.  Before the group barrier of slot u the leader waits until the store of slot u - 1 has read its
+    // buffer (cp.async.bulk.wait_group.read 0; issued a whole slot earlier), so past the barrier every buffer but
+    // slot u's is free: the leader loads slot u + kRowLnLoadAhead into one, the threads may write the next X slot.
     const int quarter = warp & 3;
     const int group = (warp - 2) >> 2;
     const int r_tile = quarter * 32 + lane;
     const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
     const int bar_id = 1 + group;
+    constexpr int kAllBar = 1 + kRowLnGroups, kAllThreads = 128 * kRowLnGroups;
+    constexpr int CPT = kRowLnChunksPerTile, XPT = kRowLnXPerTile, G = kRowLnGroups;
     uint8_t* gbufs = bufs + group * kRowLnBufs * kGemmChunkBytes;
     uint64_t* gld = ld_full + group * kRowLnBufs;
-    const int n_load = 4 * tiles_per_row, n_x = 2 * tiles_per_row, n_slots = n_load + n_x;
+    const int n_load = CPT * tiles_per_row, n_x = XPT * tiles_per_row, n_slots = n_load + n_x;
     const float inv_n = 1.0f / static_cast<float>(N);
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 
     // leader only: issue the old-residual load of slot `u` (row block u / n_slots of this CTA) if it is an L slot
-    // `prefetch_only`: pull the chunk into L2 (slot u + 6: ~4 us ahead -- a line prefetched a whole row block ahead is
-    // evicted again before its load at this streaming rate)
+    // `prefetch_only`: pull the chunk into L2 (a few us ahead -- a line prefetched a whole row block ahead is evicted
+    // again before its load at this streaming rate)
     auto issue_load = [&](int u, bool prefetch_only) {
       const int k = u / n_slots, j = u - k * n_slots;
       const int m_pair = first_pair + k * pair_step;
       if (j >= n_load || m_pair >= num_pairs_m) return;
-      const int col0 = (j >> 2) * BLOCK_N + (group + 2 * (j & 3)) * 32;
+      const int col0 = (j / CPT) * BLOCK_N + (group + G * (j % CPT)) * 32;
       const int row0 = (m_pair * 2 + cta_rank) * kGemmBlockM;
       if (prefetch_only) {
         tma_prefetch_l2_2d(&tm_r, col0, row0);
@@ -201,27 +213,26 @@ gemm_rowln_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
       mbar_expect_tx(&gld[b], kGemmChunkBytes);
       tma_load_2d(gbufs + b * kGemmChunkBytes, &tm_r, &gld[b], col0, row0);
     };
-    constexpr int kPrefetchAhead = 6;  // n_slots is 6 or 12: every L slot is exactly 6 slots after an L or X slot
+    // n_slots divides 6 * tiles_per_row * ... : with 2 groups n_slots is 6 or 12, with 4 groups 3 or 6, so slot u + 6
+    // is an L slot exactly when slot u's position in its row block is one: every L slot is prefetched once
+    constexpr int kPrefetchAhead = 6;
     if (leader) {
       for (int i = kRowLnLoadAhead; i < kPrefetchAhead; ++i) issue_load(i, true);
       for (int i = 0; i < kRowLnLoadAhead; ++i) issue_load(i, false);
     }
-    int u = 0;          // running slot count of this group
+    int u = 0;            // running slot count of this group
     uint32_t ld_par = 0;  // bit b = parity of the next load completion of buffer b
-    int stat_step = 0;    // the two statistics arrays alternate per exchange: a write follows the other array's barrier
-    int acc_first = 0;  // accumulator buffer of this row block's first tile
+    int acc_first = 0;    // accumulator buffer of this row block's first tile
     uint32_t acc_phase = 0;
-    int k_blk = 0;      // row blocks done by this CTA
-    for (int m_pair = first_pair; m_pair < num_pairs_m; m_pair += pair_step, ++k_blk) {
+    for (int m_pair = first_pair; m_pair < num_pairs_m; m_pair += pair_step) {
       const int row0 = (m_pair * 2 + cta_rank) * kGemmBlockM;
       // ---- pass 1: new residual = old + accumulator; keep it in TMEM; row sum
-      float s1 = 0.f;
+      float s1a = 0.f, s1b = 0.f;
       for (int j = 0; j < n_load; ++j, ++u) {
-        const int t = j >> 2, c = group + 2 * (j & 3);
+        const int t = j / CPT, c = group + G * (j % CPT);
         const int acc = (acc_first + t) & 1;
-        if ((j & 3) == 0) {
-          // accumulator of tile t complete
-          mbar_wait(&tmem_full[acc], acc_phase);
+        if (j % CPT == 0) {
+          mbar_wait(&tmem_full[acc], acc_phase);  // accumulator of tile t complete
           tc_fence_after();
         }
         const int b = u % kRowLnBufs;
@@ -233,82 +244,90 @@ gemm_rowln_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
         tmem_ld_32x32_raw(taddr, a);
         staging_read_row(buf, r_tile, o);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = __uint_as_float(o[i]) + __uint_as_float(a[i]);
-          s1 += v;
-          o[i] = __float_as_uint(v);
+        for (int i = 0; i < 32; i += 2) {
+          const float v0 = __uint_as_float(o[i]) + __uint_as_float(a[i]);
+          const float v1 = __uint_as_float(o[i + 1]) + __uint_as_float(a[i + 1]);
+          s1a += v0;
+          s1b += v1;
+          o[i] = __float_as_uint(v0);
+          o[i + 1] = __float_as_uint(v1);
         }
         staging_write_row(buf, r_tile, o);
         tmem_st_32x32b_x32(taddr, o);
         fence_proxy_async_smem();
+        if (leader) tma_store_wait_read<0>();  // slot u - 1's store has read its buffer (see above)
         named_bar_sync(bar_id, 128);
         if (leader) {
           tma_store_2d(&tm_r, buf, t * BLOCK_N + c * 32, row0);
           tma_store_commit();
-          tma_store_wait_read<1>();
           issue_load(u + kRowLnLoadAhead, false);
           issue_load(u + kPrefetchAhead, true);
         }
       }
-      // ---- mean, then pass 1b: centred sum of squares over this thread's chunks
-      float* st = stats + (stat_step & 1) * (2 * kGemmBlockM);
-      ++stat_step;
-      st[group * kGemmBlockM + r_tile] = s1;
-      named_bar_sync(3, 256);
-      const float mean = (st[r_tile] + st[kGemmBlockM + r_tile]) * inv_n;
-      float s2 = 0.f;
-      for (int j = 0; j < n_load; ++j) {
-        const int acc = (acc_first + (j >> 2)) & 1;
-        uint32_t a[32];
-        tmem_ld_32x32_raw(lane_base + acc * BLOCK_N + (group + 2 * (j & 3)) * 32, a);
+      // ---- mean, then pass 1b: centred sum of squares over this thread's chunks.  One statistics array: a barrier
+      // after every write AND after every read keeps the next write behind all readers.
+      stats[group * kGemmBlockM + r_tile] = s1a + s1b;
+      named_bar_sync(kAllBar, kAllThreads);
+      float tot = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float d = __uint_as_float(a[i]) - mean;
-          s2 += d * d;
+      for (int g = 0; g < G; ++g) tot += stats[g * kGemmBlockM + r_tile];
+      const float mean = tot * inv_n;
+      named_bar_sync(kAllBar, kAllThreads);
+      float s2a = 0.f, s2b = 0.f;
+      for (int j = 0; j < n_load; ++j) {
+        const int acc = (acc_first + j / CPT) & 1;
+        uint32_t a[32];
+        tmem_ld_32x32_raw(lane_base + acc * BLOCK_N + (group + G * (j % CPT)) * 32, a);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float d0 = __uint_as_float(a[i]) - mean, d1 = __uint_as_float(a[i + 1]) - mean;
+          s2a += d0 * d0;
+          s2b += d1 * d1;
         }
       }
-      st = stats + (stat_step & 1) * (2 * kGemmBlockM);
-      ++stat_step;
-      st[group * kGemmBlockM + r_tile] = s2;
-      named_bar_sync(3, 256);
-      const float rstd = 1.0f / sqrtf((st[r_tile] + st[kGemmBlockM + r_tile]) * inv_n + ln_eps);
+      stats[group * kGemmBlockM + r_tile] = s2a + s2b;
+      named_bar_sync(kAllBar, kAllThreads);
+      tot = 0.f;
+#pragma unroll
+      for (int g = 0; g < G; ++g) tot += stats[g * kGemmBlockM + r_tile];
+      const float rstd = 1.0f / sqrtf(tot * inv_n + ln_eps);
+      named_bar_sync(kAllBar, kAllThreads);
       // ---- pass 2: X = (R - mean) * rstd * w as bf16, 64 columns per slot
       for (int j = 0; j < n_x; ++j, ++u) {
-        const int xc = group + 2 * j;  // 64-column chunk of the row
+        const int xc = group + G * j;  // 64-column chunk of the row
         const int acc = (acc_first + (xc >> 2)) & 1;
         const uint32_t taddr = lane_base + acc * BLOCK_N + (xc & 3) * 64;
-        uint32_t lo[32], hi[32], w[32];
-        tmem_ld_32x32_raw(taddr, lo);
-        tmem_ld_32x32_raw(taddr + 32, hi);
-        const float4* g4 = reinterpret_cast<const float4*>(ln_w + xc * 64);
+        uint32_t w[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 ga = __ldg(g4 + i), gb = __ldg(g4 + 8 + i);
-          w[2 * i] = pack_bf16x2((__uint_as_float(lo[4 * i]) - mean) * rstd * ga.x,
-                                 (__uint_as_float(lo[4 * i + 1]) - mean) * rstd * ga.y);
-          w[2 * i + 1] = pack_bf16x2((__uint_as_float(lo[4 * i + 2]) - mean) * rstd * ga.z,
-                                     (__uint_as_float(lo[4 * i + 3]) - mean) * rstd * ga.w);
-          w[16 + 2 * i] = pack_bf16x2((__uint_as_float(hi[4 * i]) - mean) * rstd * gb.x,
-                                      (__uint_as_float(hi[4 * i + 1]) - mean) * rstd * gb.y);
-          w[16 + 2 * i + 1] = pack_bf16x2((__uint_as_float(hi[4 * i + 2]) - mean) * rstd * gb.z,
-                                          (__uint_as_float(hi[4 * i + 3]) - mean) * rstd * gb.w);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld_32x32_raw(taddr + half * 32, v);
+          const float4* g4 = reinterpret_cast<const float4*>(ln_w + xc * 64 + half * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 ga = __ldg(g4 + i);
+            w[16 * half + 2 * i] = pack_bf16x2((__uint_as_float(v[4 * i]) - mean) * rstd * ga.x,
+                                               (__uint_as_float(v[4 * i + 1]) - mean) * rstd * ga.y);
+            w[16 * half + 2 * i + 1] = pack_bf16x2((__uint_as_float(v[4 * i + 2]) - mean) * rstd * ga.z,
+                                                   (__uint_as_float(v[4 * i + 3]) - mean) * rstd * ga.w);
+          }
         }
         uint8_t* buf = gbufs + (u % kRowLnBufs) * kGemmChunkBytes;  // free: see the slot comment above
         staging_write_row(buf, r_tile, w);
         fence_proxy_async_smem();
+        if (leader) tma_store_wait_read<0>();
         named_bar_sync(bar_id, 128);
         if (leader) {
           tma_store_2d(&tm_x, buf, xc * 64, row0);
           tma_store_commit();
-          tma_store_wait_read<1>();
           issue_load(u + kRowLnLoadAhead, false);
           issue_load(u + kPrefetchAhead, true);
         }
         // ---- an accumulator goes back to the MMA warp as soon as this warp has read its last column of it
-        if (j == 1 || j == 3) {  // X slots 0,1 read tile 0, slots 2,3 tile 1 (N = 512); N = 256 has slots 0,1 only
+        if (j % XPT == XPT - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_pair_leader(&tmem_empty[(acc_first + (j >> 1)) & 1]);
+          if (lane == 0) mbar_arrive_pair_leader(&tmem_empty[(acc_first + j / XPT) & 1]);
         }
       }
       if (tiles_per_row == 2) {
