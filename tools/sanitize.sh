@@ -9,3 +9,7 @@ compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gp
 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "local_onepass or four_q_tiles or (attention_bf16_impls and 5-)" 2>&1 | tail -4
 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_forward.py -m gpu -x -q -k "tensor_core_pipeline" 2>&1 | tail -4
 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "local_onepass and 64" 2>&1 | tail -6
+# round 2 (later): four-Q-tile kernel covered above; full-row residual GEMM + LayerNorm from TMEM, RESIDUAL_LN epilogue
+compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "residual_layernorm_rows and not 76033 and not 40001" 2>&1 | tail -4
+compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "residual_layernorm_rows and 1000-512" 2>&1 | tail -6
+compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "four_q_tiles" 2>&1 | tail -6
