@@ -151,11 +151,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Lean bounded wait for the hot loops of the single-thread producer / issuer roles and the softmax warps: no clock64,
 // no printf (the call ABI of the message costs registers and a stack frame in every caller -- in a 32-register MMA
 // issuer that meant local-memory traffic on the critical path).  Each failed try_wait may suspend the thread for up to
-// the 10 ms hint, so 1024 of them bound a hung protocol to seconds; then the kernel traps (the host sees an error).
+// the 10 ms hint; a hung protocol ends in a trap (the host sees an error).
+// After 1024 polls the wait goes on bounded by TIME (2^31 cycles, ~1 s) on the 32-bit clock, inline (a call would need
+// ABI registers the setmaxnreg kernels do not have): under compute-sanitizer a failed try_wait returns at once
+// instead of suspending, and a count-only bound trapped kernels that were merely slow.
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   uint32_t tries = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++tries > 1024u) __trap();
+    if (++tries > 1024u) {
+      const uint32_t t0 = static_cast<uint32_t>(clock());
+      while (!mbar_try_wait(bar, parity)) {
+        if (static_cast<uint32_t>(clock()) - t0 > 0x7fffffffu) __trap();
+      }
+      return;
+    }
   }
 }
 // The same primitives on 32-bit shared-window addresses computed ONCE per kernel (smem_u32 of the barrier block +
@@ -180,7 +189,13 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
   uint32_t tries = 0;
   while (!mbar_try_wait_a(bar, parity)) {
-    if (++tries > 1024u) __trap();
+    if (++tries > 1024u) {
+      const uint32_t t0 = static_cast<uint32_t>(clock());
+      while (!mbar_try_wait_a(bar, parity)) {
+        if (static_cast<uint32_t>(clock()) - t0 > 0x7fffffffu) __trap();
+      }
+      return;
+    }
   }
 }
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
