@@ -46,6 +46,7 @@ GEMM_SHAPES = [
     (4113, 1536, 512),
     (257, 256, 2048),
     (20000, 768, 256),
+    (19201, 512, 512),  # >= one 256-row block per CTA pair, K <= 512: the A-stationary pair kernel (ragged last block)
     (1, 128, 64),
 ]
 
@@ -112,7 +113,7 @@ def _rope_ref(qkv: torch.Tensor, pos: torch.Tensor, cos: torch.Tensor, sin: torc
     return x.view(t, 3 * hidden)
 
 
-@pytest.mark.parametrize("m,hidden", [(333, 128), (1500, 256), (2000, 512), (76033, 256)])  # last: row-grouped tile order
+@pytest.mark.parametrize("m,hidden", [(333, 128), (1500, 256), (2000, 512), (76033, 256), (19300, 512)])  # last two: row-grouped tile order
 def test_gemm_bf16_rope(m, hidden, gemm_kernel):
     a = _rand_bf16((m, hidden), 6)
     w = _rand_bf16((3 * hidden, hidden), 7, 0.05)
@@ -126,7 +127,8 @@ def test_gemm_bf16_rope(m, hidden, gemm_kernel):
     _bf16_close(out, ref, f"gemm rope m={m} H={hidden}")
 
 
-@pytest.mark.parametrize("m,k,inter", [(300, 128, 128), (1000, 512, 2048), (4113, 256, 1152)])
+@pytest.mark.parametrize("m,k,inter", [(300, 128, 128), (1000, 512, 2048), (4113, 256, 1152), (19201, 512, 2048),
+                                       (40000, 256, 1024)])  # the last two: A-stationary pair kernel
 def test_gemm_bf16_geglu(m, k, inter, gemm_kernel):
     a = _rand_bf16((m, k), 9)
     wi = _rand_bf16((2 * inter, k), 10, 0.08)
