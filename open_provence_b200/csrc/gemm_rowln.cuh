@@ -15,17 +15,17 @@
 // HBM bytes per token: A + 4N (old) + 4N (new) + 2N (X) against A + 8N + (4N + 2N) for GEMM + LayerNorm launches.
 //
 // Same producer / MMA-issuer structure as gemm_bf16_tcgen05_pair_kernel (cta_group::2, 256 x 256 tiles, group_rows
-// tile order); 3 operand stages, 8 epilogue warps in 2 column groups with four 16 KB buffers each (load -> modify in
-// place -> store, three loads ahead).
+// tile order); 4 operand stages, 8 epilogue warps in 2 column groups with three 16 KB buffers each (load -> modify in
+// place -> store, two loads ahead).  Measured, attn.Wo per step: 3 stages + 4 buffers 3.40-3.45 ms, 4 + 3: 3.27-3.35.
 #pragma once
 
 #include "gemm_tcgen05.cuh"
 
 namespace opv {
 
-constexpr int kRowLnStages = 3;
+constexpr int kRowLnStages = 4;
 constexpr int kRowLnGroups = 2;                  // epilogue groups of 4 warps; group g takes the 32-column chunks c = g (mod groups). Measured with 4 groups (16 warps, 2 buffers each, one load ahead): attn.Wo 3.45 -> 3.92 ms per step -- the depth of the load pipeline matters, not the number of warps
-constexpr int kRowLnBufs = 8 / kRowLnGroups;     // 16 KB buffers per epilogue group (8 in total)
+constexpr int kRowLnBufs = 3;                    // 16 KB buffers per epilogue group
 constexpr int kRowLnLoadAhead = kRowLnBufs - 1;  // old-residual loads in flight per group
 constexpr int kRowLnThreads = 64 + 128 * kRowLnGroups;
 constexpr int kRowLnChunksPerTile = 8 / kRowLnGroups;  // "L" slots per 256-column tile and group
@@ -34,8 +34,8 @@ constexpr int kRowLnXPerTile = 4 / kRowLnGroups;       // "X" slots per tile and
 struct RowLnSmemLayout {
   static constexpr int kStageA = kGemmBlockM * kGemmBlockK * 2;
   static constexpr int kStageB = 128 * kGemmBlockK * 2;
-  static constexpr int kTileBytes = kRowLnStages * (kStageA + kStageB);  //  96 KB
-  static constexpr int kBufBytes = kRowLnGroups * kRowLnBufs * kGemmChunkBytes;  // 128 KB
+  static constexpr int kTileBytes = kRowLnStages * (kStageA + kStageB);  // 128 KB
+  static constexpr int kBufBytes = kRowLnGroups * kRowLnBufs * kGemmChunkBytes;  //  96 KB
   static constexpr int kStatBytes = kRowLnGroups * kGemmBlockM * 4;      // [group][row] fp32 partial sums
   static constexpr int kBarrierBytes = 192;
   // no alignment slack: the dynamic segment is the kernel's only shared memory and starts 1024-aligned (checked)
