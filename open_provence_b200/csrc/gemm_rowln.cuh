@@ -16,7 +16,8 @@
 //
 // Same producer / MMA-issuer structure as gemm_bf16_tcgen05_pair_kernel (cta_group::2, 256 x 256 tiles, group_rows
 // tile order); 4 operand stages, 8 epilogue warps in 2 column groups with three 16 KB buffers each (load -> modify in
-// place -> store, two loads ahead).  Measured, attn.Wo per step: 3 stages + 4 buffers 3.40-3.45 ms, 4 + 3: 3.27-3.35.
+// place -> store, two loads ahead).  Measured, attn.Wo per step: 3 stages + 4 buffers 3.40-3.45 ms, 4 + 3: 3.27-3.35,
+// 5 + 2 (one load ahead): 4.04.
 #pragma once
 
 #include "gemm_tcgen05.cuh"
