@@ -39,8 +39,7 @@ struct RowLnSmemLayout {
   static constexpr int kBufBytes = kRowLnGroups * kRowLnBufs * kGemmChunkBytes;  //  96 KB
   static constexpr int kStatBytes = kRowLnGroups * kGemmBlockM * 4;      // [group][row] fp32 partial sums
   static constexpr int kBarrierBytes = 192;
-  // no alignment slack: the dynamic segment is the kernel's only shared memory and starts 1024-aligned (checked)
-  static constexpr int kTotal = kTileBytes + kBufBytes + kStatBytes + kBarrierBytes;
+  static constexpr int kTotal = kTileBytes + kBufBytes + kStatBytes + kBarrierBytes + 1024;  // + alignment slack
   static constexpr int kTmemCols = 512;
 };
 static_assert(RowLnSmemLayout::kTotal <= 232448, "row-LN GEMM: shared memory budget");
@@ -68,8 +67,9 @@ gemm_rowln_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_co
                        const int K) {
   using L = RowLnSmemLayout;
   constexpr int BLOCK_N = 256;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw0 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw0 + 1023u) & ~1023u) - raw0);  // 1024-aligned in the shared address space
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kRowLnStages * L::kStageA;
   uint8_t* bufs = smem + L::kTileBytes;                                      // [group][kRowLnBufs] x 16 KB
