@@ -125,6 +125,16 @@ int opv_forward_packed(opv_handle h, const int32_t* d_ids, const int32_t* d_cu_s
                        int64_t n_tokens, int32_t max_seqlen, float* d_prune_logits, float* d_rank_logits,
                        void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* cu_seqlens is read on the device only.  The forward never trusts it for addressing: its first kernel clamps every
+ * boundary into [0, n_tokens] (later kernels read the clamped copy; a malformed array gives wrong results for the
+ * sequences concerned, never an out-of-bounds access) and records per sequence whether the boundaries were
+ * 0 <= begin <= end <= n_tokens, end - begin <= max_seqlen, first begin == 0, last end == n_tokens.
+ * opv_forward_status() synchronises `stream` and counts the sequences of the LAST opv_forward_packed() call with that
+ * workspace and those sizes that broke the contract (0 = the input was well formed).  The reference's equivalent is
+ * the attention_mask handed to `OpenProvenceModel.forward` (standalone:1666-1699), which it does not validate either. */
+int opv_forward_status(opv_handle engine, const void* d_workspace, int32_t n_seqs, int64_t n_tokens,
+                       int32_t* n_bad_sequences, void* stream);
+
 /* Tuning switches (tests, profiling).  opv_set_option() edits the process-wide DEFAULTS: every engine snapshots them
  * at opv_create(), the single-op entry points (opv_op_*) read them at call time; opv_engine_set_option() changes one
  * engine only (everything except "gemm_pair", which is fixed at creation).  Both are thread-safe.

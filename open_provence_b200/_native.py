@@ -158,6 +158,7 @@ SIGNATURES = {
     "opv_pack_build": (C.c_int, [C.POINTER(OpvPackInput), C.POINTER(C.c_void_p)]),
     "opv_pack_view_get": (C.c_int, [C.c_void_p, C.POINTER(OpvPackView)]),
     "opv_pack_destroy": (C.c_int, [C.c_void_p]),
+    "opv_forward_status": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "opv_op_gemm_residual_ln": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_int32, C.c_int32,

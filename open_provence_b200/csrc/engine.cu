@@ -630,7 +630,7 @@ struct LaunchScope {
 };
 
 struct WorkspaceLayout {
-  size_t h, x, qkv, attn, act, u, pos, cls, y, pool, split, total;
+  size_t h, x, qkv, attn, act, u, pos, cu, status, cls, y, pool, split, total;
 };
 
 static WorkspaceLayout workspace_layout(const opv_engine* e, int64_t T, int64_t n_seqs) {
@@ -652,6 +652,8 @@ static WorkspaceLayout workspace_layout(const opv_engine* e, int64_t T, int64_t 
   l.u = take(unfused ? rows * 2 * I * elt : 0);
   l.pos = take(rows * 4);
   const size_t seqs = static_cast<size_t>(n_seqs > 0 ? n_seqs : 1);
+  l.cu = take((seqs + 1) * 4);  // cu_seqlens clamped into [0, T] (positions_checked_kernel)
+  l.status = take(seqs * 4);    // per sequence: 1 = its boundaries were not what the contract says
   l.cls = take(seqs * H * 4);  // rank head: LN(CLS row)
   l.y = take(seqs * H * 4);    // rank head: gelu(dense(cls))
   // mean pooling: per-chunk sums of the final-normed rows (slot = begin / chunk + s + c, pointwise.cuh)
@@ -819,11 +821,15 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
     ~ForwardTokens() { t_forward_tokens = 0; }
   } forward_tokens(T);
 
+  // every later kernel reads the clamped copy: a malformed cu_seqlens gives wrong results, never an out-of-bounds access
+  int32_t* cu_clean = reinterpret_cast<int32_t*>(ws + wl.cu);
   {
     LaunchScope sc(e, stream, OPV_PROF_MISC);
-    opv::positions_kernel<<<n_seqs, 256, 0, stream>>>(d_cu_seqlens, pos);
-    OPV_LAUNCH_CHECK("positions_kernel");
+    opv::positions_checked_kernel<<<n_seqs, 256, 0, stream>>>(d_cu_seqlens, cu_clean, reinterpret_cast<int32_t*>(ws + wl.status),
+                                                             pos, T, max_seqlen, c.max_positions);
+    OPV_LAUNCH_CHECK("positions_checked_kernel");
   }
+  d_cu_seqlens = cu_clean;
 
   if (c.dtype == OPV_DTYPE_BF16) {
     using bf16 = __nv_bfloat16;
@@ -877,7 +883,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       }
       if (rc) return rc;
       opv::GemmEpilogueArgs ep{};
-      ep.pos = pos, ep.rope_cols = 2 * H;
+      ep.pos = pos, ep.rope_cols = 2 * H, ep.rope_rows = c.max_positions;
       ep.cos = global ? e->w.d_rope_cos_global : e->w.d_rope_cos_local;
       ep.sin = global ? e->w.d_rope_sin_global : e->w.d_rope_sin_local;
       {
@@ -887,7 +893,8 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       if (rc) return rc;
       if (!fused) {
         LaunchScope sc(e, stream, OPV_PROF_MISC);
-        opv::rope_inplace_kernel<bf16><<<g_num_sms * 8, 256, 0, stream>>>(static_cast<bf16*>(qkv), pos, ep.cos, ep.sin, T, H);
+        opv::rope_inplace_kernel<bf16><<<g_num_sms * 8, 256, 0, stream>>>(static_cast<bf16*>(qkv), pos, ep.cos, ep.sin, T, H,
+                                                                          c.max_positions);
         OPV_LAUNCH_CHECK("rope_inplace_kernel");
       }
       {
@@ -995,7 +1002,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
         LaunchScope sc(e, stream, OPV_PROF_MISC);
         opv::rope_inplace_kernel<float><<<g_num_sms * 8, 256, 0, stream>>>(
             qf, pos, global ? e->w.d_rope_cos_global : e->w.d_rope_cos_local,
-            global ? e->w.d_rope_sin_global : e->w.d_rope_sin_local, T, H);
+            global ? e->w.d_rope_sin_global : e->w.d_rope_sin_local, T, H, c.max_positions);
         OPV_LAUNCH_CHECK("rope_inplace_kernel");
       }
       {
@@ -1049,7 +1056,7 @@ int opv_forward_packed(opv_handle e, const int32_t* d_ids, const int32_t* d_cu_s
       OPV_LAUNCH_CHECK("rank_head_mean_finish_kernel");
       e->launches += 1;  // one launch more than the "cls" head
     } else {
-      opv::rank_head_cls_ln_kernel<<<n_seqs, 32, 0, stream>>>(h, d_cu_seqlens, e->w.d_final_norm, cls, H, c.norm_eps);
+      opv::rank_head_cls_ln_kernel<<<n_seqs, 32, 0, stream>>>(h, d_cu_seqlens, e->w.d_final_norm, cls, H, c.norm_eps, T);
       OPV_LAUNCH_CHECK("rank_head_cls_ln_kernel");
     }
     {
@@ -1131,6 +1138,25 @@ int opv_sentence_prune(const float* d_frag_mean, const int32_t* d_sent_offsets, 
 }
 
 // ---- single-op entry points -----------------------------------------------------------------------
+
+int opv_forward_status(opv_handle e, const void* d_workspace, int32_t n_seqs, int64_t n_tokens, int32_t* n_bad,
+                       void* stream_) {
+  if (!e || !d_workspace || !n_bad) return fail(OPV_ERR_INVALID_ARGUMENT, "opv_forward_status: null argument");
+  *n_bad = 0;
+  if (n_seqs <= 0 || n_tokens <= 0) return OPV_OK;
+  DeviceGuard guard;
+  OPV_CUDA(guard.enter(e->device));
+  const WorkspaceLayout wl = workspace_layout(e, n_tokens, n_seqs);
+  const uint8_t* ws = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(d_workspace) + 1023) & ~uintptr_t(1023));
+  std::vector<int32_t> status(static_cast<size_t>(n_seqs));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  OPV_CUDA(cudaMemcpyAsync(status.data(), ws + wl.status, status.size() * 4, cudaMemcpyDeviceToHost, stream));
+  OPV_CUDA(cudaStreamSynchronize(stream));
+  int bad = 0;
+  for (int32_t v : status) bad += v != 0;
+  *n_bad = bad;
+  return OPV_OK;
+}
 
 int opv_op_gemm(int32_t dtype, int32_t epilogue, const void* d_a, const void* d_w, void* d_c, int64_t m, int32_t n,
                 int32_t k, const int32_t* d_pos, const float* d_cos, const float* d_sin, int32_t hidden_size,

@@ -46,6 +46,7 @@ struct GemmEpilogueArgs {
   const float* cos;    // ROPE: [max_pos, 32]
   const float* sin;    // ROPE: [max_pos, 32]
   int32_t rope_cols;   // ROPE: output columns < rope_cols (= 2H: q and k) are rotated
+  int32_t rope_rows;   // ROPE: rows of the cos / sin tables; positions are clamped into [0, rope_rows) (0 = trusted)
   // CTA-pair kernel, ROPE: 1 = a cluster takes ALL column tiles of a 256-row block before moving to its next row
   // block, so the rows' cos|sin table lines are staged once per row block instead of once per rotated tile
   // (set by the host when there are at least as many row blocks as clusters)
@@ -140,7 +141,8 @@ __device__ __forceinline__ void rope_stage_rows(const GemmEpilogueArgs& ep, uint
   for (int it = 0; it < 8; ++it) {
     const int r = it * 16 + (epi_tid >> 4);
     const int64_t row = static_cast<int64_t>(row0) + r;
-    const int p = row < M ? __ldg(ep.pos + row) : 0;
+    int p = row < M ? __ldg(ep.pos + row) : 0;
+    if (ep.rope_rows > 0) p = min(max(p, 0), ep.rope_rows - 1);  // rows no sequence covers hold no position
     const float* src = (piece < 8 ? ep.cos : ep.sin) + static_cast<int64_t>(p) * 32 + (piece & 7) * 4;
     const float4 v = __ldg(reinterpret_cast<const float4*>(src));
     *reinterpret_cast<float4*>(rope_cs + r * kRopeRowBytes + ((piece ^ (r & 7)) << 4)) = v;

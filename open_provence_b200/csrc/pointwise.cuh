@@ -161,9 +161,11 @@ constexpr int kRankFeatTile = 8;  // = warps per CTA of stage 2
 
 __global__ void __launch_bounds__(32)
 rank_head_cls_ln_kernel(const float* __restrict__ h, const int32_t* __restrict__ cu_seqlens,
-                        const float* __restrict__ final_norm, float* __restrict__ cls, const int H, const float eps) {
+                        const float* __restrict__ final_norm, float* __restrict__ cls, const int H, const float eps,
+                        const int64_t M) {
   const int s = blockIdx.x, lane = threadIdx.x;
-  const float* row = h + static_cast<int64_t>(cu_seqlens[s]) * H;
+  const int64_t first = cu_seqlens[s];
+  const float* row = h + (first < M ? first : M - 1) * H;  // an empty trailing sequence must not read past the buffer
   const float inv_h = 1.0f / static_cast<float>(H);
   float part = 0.f;
   for (int i = lane; i < H; i += 32) part += row[i];
@@ -305,13 +307,36 @@ __global__ void positions_kernel(const int32_t* __restrict__ cu_seqlens, int32_t
   for (int i = begin + threadIdx.x; i < end; i += blockDim.x) pos[i] = i - begin;
 }
 
+// The forward's version: cu_seqlens is a DEVICE array the host cannot look at without a synchronisation, so it is made
+// memory-safe here instead of trusted.  cu_clean[s] = clamp(cu_seqlens[s], 0, T) is what every later kernel reads: all
+// row indices derived from it stay inside [0, T) (a non-increasing pair is an empty sequence to them), positions stay
+// inside the RoPE table.  status[s] != 0 marks a boundary pair that was not 0 <= begin <= end <= T with
+// end - begin <= max_seqlen, first begin == 0, last end == T; opv_forward_status() counts them on request.
+__global__ void positions_checked_kernel(const int32_t* __restrict__ cu_seqlens, int32_t* __restrict__ cu_clean,
+                                         int32_t* __restrict__ status, int32_t* __restrict__ pos, const int64_t T,
+                                         const int max_seqlen, const int max_pos) {
+  const int s = blockIdx.x, last = gridDim.x - 1;
+  const int64_t b0 = cu_seqlens[s], e0 = cu_seqlens[s + 1];
+  const int begin = static_cast<int>(b0 < 0 ? 0 : (b0 > T ? T : b0));
+  const int end = static_cast<int>(e0 < 0 ? 0 : (e0 > T ? T : e0));
+  if (threadIdx.x == 0) {
+    cu_clean[s] = begin;
+    if (s == last) cu_clean[s + 1] = end;
+    status[s] = (b0 != begin || e0 != end || e0 < b0 || e0 - b0 > max_seqlen || (s == 0 && b0 != 0) ||
+                 (s == last && e0 != T))
+                    ? 1
+                    : 0;
+  }
+  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) pos[i] = min(i - begin, max_pos - 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // unfused RoPE (in place on the q,k thirds of qkv [M, 3H]) and GeGLU -- fp32 parity mode
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void rope_inplace_kernel(T* __restrict__ qkv, const int32_t* __restrict__ pos,
                                     const float* __restrict__ cos_t, const float* __restrict__ sin_t, const int64_t M,
-                                    const int H) {
+                                    const int H, const int max_pos = 0) {
   const int heads2 = 2 * (H / 64);  // q heads then k heads: contiguous first 2H columns
   const int64_t total = M * heads2 * 32;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -320,7 +345,8 @@ __global__ void rope_inplace_kernel(T* __restrict__ qkv, const int32_t* __restri
     const int64_t rh = idx >> 5;
     const int hd = static_cast<int>(rh % heads2);
     const int64_t row = rh / heads2;
-    const int p = pos[row];
+    int p = pos[row];
+    if (max_pos > 0) p = min(max(p, 0), max_pos - 1);  // rows no sequence covers hold no position
     const float c = cos_t[static_cast<int64_t>(p) * 32 + i], s = sin_t[static_cast<int64_t>(p) * 32 + i];
     T* base = qkv + row * (3 * static_cast<int64_t>(H)) + hd * 64;
     const float a = OperandCast<T>::to_float(base[i]), b = OperandCast<T>::to_float(base[i + 32]);

@@ -288,7 +288,21 @@ class Engine:
                 prune.data_ptr(), rank.data_ptr(), ws.data_ptr(), ws.numel(), self._stream(),
             )
         N.check(rc, "opv_forward_packed")
+        self._last_forward = (ws, n_seqs, n_tokens)
         return prune, rank
+
+    def forward_status(self) -> int:
+        """Number of sequences of the last ``forward_packed`` call whose ``cu_seqlens`` boundaries broke the contract
+        (0 = well formed).  The forward itself clamps them and stays memory-safe; this synchronises the stream."""
+        last = getattr(self, "_last_forward", None)
+        if last is None:
+            return 0
+        ws, n_seqs, n_tokens = last
+        bad = N.C.c_int32(0)
+        with torch.cuda.device(self.device):
+            rc = self.lib.opv_forward_status(self._handle, ws.data_ptr(), n_seqs, n_tokens, N.C.byref(bad), self._stream())
+        N.check(rc, "opv_forward_status")
+        return int(bad.value)
 
     def fragment_means(
         self, prune_logits: torch.Tensor, frag_ranges: torch.Tensor, rank_logits: torch.Tensor

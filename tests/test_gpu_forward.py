@@ -97,6 +97,39 @@ def test_forward_is_deterministic_and_batch_invariant(tiny_ckpt_dir, tiny_config
     assert torch.equal(rank_all[b : b + 1], rank_one)
 
 
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_malformed_cu_seqlens_is_clamped_on_the_device_and_reported(tiny_ckpt_dir, tiny_config, forward_golden, dtype):
+    """``cu_seqlens`` lives on the device: the forward clamps it there instead of trusting it (no out-of-bounds access
+    whatever it holds -- tools/sanitize.sh runs this test under memcheck) and ``forward_status`` reports how many
+    sequences broke the contract.  Well-formed sequences next to a broken one keep their exact results."""
+    eng = Engine(tiny_config["base_model_config"], _state_dict(tiny_ckpt_dir), device=DEV, dtype=dtype,
+                 num_labels=len(tiny_config.get("id2label") or {0: 0}))
+    ids, cu, lengths = _pack(forward_golden)
+    prune_ok, rank_ok = eng.forward_packed(ids, cu, max(lengths))
+    assert eng.forward_status() == 0
+    T = int(ids.numel())
+    # last boundary far past the buffer, one negative, one pair decreasing, a first boundary that is not 0
+    for bad_cu, n_bad_min in (
+        ([0] + [int(v) for v in cu[1:-1]] + [T + 100000], 1),
+        ([0, -5] + [int(v) for v in cu[2:]], 2),
+        ([0, int(cu[2]), int(cu[1])] + [int(v) for v in cu[3:]], 1),
+        ([3] + [int(v) for v in cu[1:]], 1),
+        ([2**31 - 1] * len(cu), len(lengths)),
+    ):
+        bad = torch.tensor(bad_cu, dtype=torch.int32, device=DEV)
+        prune, rank = eng.forward_packed(ids, bad, max(lengths))
+        torch.cuda.synchronize()  # a device fault would surface here
+        assert eng.forward_status() >= n_bad_min, bad_cu
+    # the first case only breaks the LAST sequence: every other sequence is bit-identical to the clean run
+    bad = torch.tensor([0] + [int(v) for v in cu[1:-1]] + [T + 100000], dtype=torch.int32, device=DEV)
+    prune, rank = eng.forward_packed(ids, bad, max(lengths))
+    torch.cuda.synchronize()
+    assert torch.equal(prune, prune_ok) and torch.equal(rank, rank_ok)  # clamped to T: the same sequences after all
+    prune_again, rank_again = eng.forward_packed(ids, cu, max(lengths))
+    assert eng.forward_status() == 0
+    assert torch.equal(prune_again, prune_ok) and torch.equal(rank_again, rank_ok)
+
+
 def test_bf16_engine_against_the_references_own_bf16_forward(tiny_ckpt_dir, tiny_config, forward_golden):
     """north_star's bf16 bar is stated against the reference forward.  The reference's own bf16 forward
     (tests/golden/make_golden_bf16.py: bf16 weights, bf16 residual stream, bf16 RoPE tables) is itself

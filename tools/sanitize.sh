@@ -13,3 +13,5 @@ compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_g
 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "residual_layernorm_rows and not 76033 and not 40001" 2>&1 | tail -4
 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "residual_layernorm_rows and 1000-512" 2>&1 | tail -6
 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "four_q_tiles" 2>&1 | tail -6
+# malformed cu_seqlens (boundaries past the buffer, negative, decreasing): clamped on the device, no out-of-bounds access
+compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_forward.py -m gpu -x -q -k "malformed" 2>&1 | tail -4
